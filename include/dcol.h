@@ -1,0 +1,147 @@
+/*
+ * dcol.h — C ABI of the B200-native batched DCOL proximity solve + gradient.
+ *
+ * This is the drop-in boundary for ONE path of CogSP/DCOL-trajectory-optimization: the
+ * primal-dual interior-point proximity solve and its pose gradient.  Every entry point
+ * replaces a piece of the reference's Python call chain (paths relative to the reference
+ * root):
+ *
+ *   dcol_shape / dcol_shape_table_*   primitive attribute bags + isinstance dispatch
+ *                                     primitives/misc_primitive_constructor.py:4-88
+ *                                     primitives/problem_matrices.py:255-364
+ *   dcol_plan_*                       (new) grouping of a batch by type signature; the
+ *                                     reference loops pair by pair
+ *                                     (systems/cluttered_hallway_quadrotor.py:131-133,155)
+ *   dcol_proximity_batch_{device,host}
+ *                                     proximity_mrp            proximity/proximity.py:6-54
+ *                                     proximity_gradient       proximity/proximity_gradient.py:91-138
+ *                                     problem_matrices         primitives/problem_matrices.py:4-364
+ *                                     combine_problem_matrices primitives/combine_problem_matrices.py:3-70
+ *                                     solve_lp_pdip            proximity/pdip.py:373-470
+ *                                     calc_NT_scalings & co    proximity/NT/NT_scaling.py:75-126,205-240,340-463
+ *                                     obj_val_grad             proximity/proximity_gradient.py:50-88
+ *
+ * All arithmetic is IEEE-754 binary64.  Plain pointers and sizes only; no torch types.
+ * Functions returning int return 0 on success, a negative DCOL_E_* code for argument
+ * errors, or a positive cudaError_t; dcol_last_error() describes the last failure of the
+ * calling thread.  Per-pair solver outcomes are NOT errors: they are reported in status[].
+ */
+#ifndef DCOL_H_
+#define DCOL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCOL_ABI_VERSION 1
+
+/* primitive kinds (order of SURVEY.md section 8) */
+enum {
+    DCOL_POLYTOPE = 0, /* {y : A y <= alpha b}, f faces            problem_matrices.py:181-209 */
+    DCOL_CAPSULE  = 1, /* radius R, segment length L (body x axis) problem_matrices.py:4-44    */
+    DCOL_CYLINDER = 2, /* radius R, length L                       problem_matrices.py:47-87   */
+    DCOL_CONE     = 3, /* height H, half angle beta                problem_matrices.py:125-148 */
+    DCOL_SPHERE   = 4, /* radius R                                 problem_matrices.py:151-178 */
+    DCOL_POLYGON  = 5, /* planar {A y <= alpha b} padded by R      problem_matrices.py:90-120  */
+    DCOL_N_KINDS  = 6
+};
+
+#define DCOL_MAX_FACES 32 /* most half-spaces of one polytope / polygon */
+#define DCOL_MAX_ITER  50 /* the reference's hard-coded loop cap, pdip.py:408 */
+
+/* per-pair status: the reference signals these by exception class */
+enum {
+    DCOL_STATUS_OK          = 0,
+    DCOL_STATUS_MAX_ITER    = 1, /* Exception("Maximum number of iterations reached, PDIP failed"), pdip.py:470 */
+    DCOL_STATUS_NON_FINITE  = 2, /* ValueError("array must not contain infs or NaNs") from SciPy check_finite  */
+    DCOL_STATUS_NOT_PD      = 3, /* numpy.linalg.LinAlgError from a Cholesky factorisation                      */
+    DCOL_STATUS_UNSUPPORTED = 4  /* ValueError from np.vstack: both primitives carry extra variables,
+                                    combine_problem_matrices.py:58-67                                          */
+};
+
+/* argument errors */
+enum {
+    DCOL_E_ARG     = -1, /* null pointer / negative size / bad flag  */
+    DCOL_E_SHAPE   = -2, /* malformed shape record                   */
+    DCOL_E_INDEX   = -3, /* shape index out of range                 */
+    DCOL_E_NOGPU   = -4  /* no CUDA device (there is no CPU fallback) */
+};
+
+/* output selection */
+enum {
+    DCOL_WANT_CONTACT = 1u, /* x[0:3] of the solution, proximity.py:52                        */
+    DCOL_WANT_GRAD    = 2u  /* d alpha / d [r1 p1 r2 p2], proximity_gradient.py:71-77 layout  */
+};
+
+/* One primitive SHAPE (no pose).  144 bytes, natural alignment. */
+typedef struct dcol_shape {
+    int32_t type;        /* DCOL_POLYTOPE .. DCOL_POLYGON                              */
+    int32_t n_faces;     /* polytope / polygon: number of half-spaces, otherwise 0     */
+    int32_t face_off;    /* first face of this shape in the packed A / b arrays        */
+    int32_t reserved;
+    double  R, L, H, beta;
+    double  r_offset[3]; /* body-frame offset of the primitive's origin                */
+    double  Q_offset[9]; /* body-frame rotation offset, row-major                      */
+} dcol_shape;
+
+typedef struct dcol_shape_table dcol_shape_table; /* device-resident copy of a shape list */
+typedef struct dcol_plan dcol_plan;               /* a batch's pairs grouped by type signature */
+
+const char* dcol_version(void);
+const char* dcol_last_error(void);
+int         dcol_device_count(void);
+
+/* Upload n_shapes records and the packed half-space arrays A[n_faces][3] (polygons use the
+ * first two columns), b[n_faces] to `device`.  Host pointers. */
+int  dcol_shape_table_create(const dcol_shape* shapes, int32_t n_shapes, const double* A, const double* b,
+                             int32_t n_faces, int device, dcol_shape_table** out);
+void dcol_shape_table_destroy(dcol_shape_table* table);
+
+/* Group B pairs by type signature (kind1, kind2, faces1, faces2) with a device counting sort.
+ * idx1 / idx2 are DEVICE pointers to int32 shape indices.  The plan can be reused for any
+ * number of solves over the same index arrays (ALTRO re-evaluates a fixed set of
+ * victim x obstacle pairs with new poses every iteration).  Synchronises `stream` once. */
+int     dcol_plan_create(const dcol_shape_table* table, const int32_t* d_idx1, const int32_t* d_idx2, int64_t B,
+                         void* stream, dcol_plan** out);
+void    dcol_plan_destroy(dcol_plan* plan);
+int64_t dcol_plan_size(const dcol_plan* plan);
+int32_t dcol_plan_n_groups(const dcol_plan* plan);
+/* Kernel launches one solve over this plan enqueues. */
+int32_t dcol_plan_n_launches(const dcol_plan* plan);
+
+/* Solve every pair of the plan.  All pointers are DEVICE pointers; the call only enqueues work
+ * on `stream` (a cudaStream_t, may be NULL for the default stream).
+ *   pose1, pose2 : [B][6] rows (r, p)
+ *   alpha        : [B]
+ *   contact      : [B][3]   or NULL unless DCOL_WANT_CONTACT
+ *   grad         : [B][12]  or NULL unless DCOL_WANT_GRAD
+ *   iters,status : [B] int32 (PDIP iterations taken; DCOL_STATUS_*)
+ * tol is the reference's pdip_tol (1e-6 at both call sites); max_iter must be in 1..DCOL_MAX_ITER
+ * (the reference always runs with 50). */
+int dcol_proximity_batch_device(const dcol_plan* plan, const double* d_pose1, const double* d_pose2, double tol,
+                                int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact,
+                                double* d_grad, int32_t* d_iters, int32_t* d_status, void* stream);
+
+/* Same computation with HOST buffers: allocates device scratch, copies in, plans, solves,
+ * copies out, synchronises.  This is the call a reference-side binding makes. */
+int dcol_proximity_batch_host(const dcol_shape_table* table, const int32_t* idx1, const int32_t* idx2,
+                              const double* pose1, const double* pose2, int64_t B, double tol, int32_t max_iter,
+                              uint32_t flags, double* alpha, double* contact, double* grad, int32_t* iters,
+                              int32_t* status);
+
+/* Debug aid: solve ONE pair and also return the per-iteration mu = s'z/deg trace
+ * (mu_trace[DCOL_MAX_ITER + 1], NaN padded) and the final (x[8], s[72], z[72]).  Host pointers. */
+int dcol_debug_trace_pair(const dcol_shape_table* table, int32_t idx1, int32_t idx2, const double* pose1,
+                          const double* pose2, double tol, double* alpha, double* x, double* s, double* z,
+                          int32_t* n, int32_t* m, int32_t* iters, int32_t* status, double* mu_trace);
+
+/* Measured FP64 FMA throughput of `device` in FLOP/s (dependent-chain-free DFMA loop, all SMs),
+ * the roofline denominator MEASURED_PEAKS.json lacks. */
+int dcol_measure_fp64_peak(int device, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCOL_H_ */
