@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the batched DCOL proximity solve + gradient (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
+
+One step = one pass of the hot path (alpha + contact point + d alpha / d pose for every pair) over
+one batch of the config-4 workload ("synthetic batched proximity sweep": all 40 reference-supported
+ordered type pairs over the 7-shape table, random poses), P pairs per GPU (weak scaling), followed
+for N > 1 by the single all-gather of every rank's records.  Rank 0 prints ONE JSON line.
+
+ value          pairs/s, whole job, inputs resident in HBM, timed with CUDA events, max over ranks
+ e2e            the same metric through the host entry point of the C ABI (dcol_proximity_batch_host):
+                page-locked NumPy buffers in and out, host<->device copies inside the timed region
+ roofline       FP64: algorithmic flops (actual iteration counts) of the
+                pair_kernel launches / their CUDA-event duration / the FP64 FMA peak measured in
+                this run (dcol_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 entry)
+ cpu_baseline   the oracle (C port of the reference's NumPy path, all host threads) on a bounded
+                sample of the same workload; rank 0, N = 1 only
+ --impl reference   times that CPU path alone, same metric / config
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "proximity solves+grads/sec"
+UNIT = "pairs/s"
+WORKLOAD = "config4: synthetic batched proximity sweep, 40 ordered type pairs x random poses, alpha + contact + grad[12]"
+
+
+def make_batch(n_pairs, seed):
+    from dcol_trajectory_optimization_b200 import workloads as W
+    from dcol_trajectory_optimization_b200.shapes import flatten_shapes
+    shapes, i1, i2, p1, p2 = W.config4_batch(n_pairs, seed=seed)
+    return flatten_shapes(shapes), i1, i2, p1, p2
+
+
+def flop_model_total(rec, i1, i2, iters):
+    """Sum over pairs of the algorithmic flop model with each pair's actual iteration count."""
+    from dcol_trajectory_optimization_b200.shapes import POLYTOPE, flop_model, problem_dims
+    ns = len(rec)
+    key = i1.astype(np.int64) * ns + i2
+    cnt = np.bincount(key, minlength=ns * ns)
+    its = np.bincount(key, weights=iters.astype(np.float64), minlength=ns * ns)
+    total = 0.0
+    for k in np.nonzero(cnt)[0]:
+        r1, r2 = rec[k // ns], rec[k % ns]
+        m_ort, q1, q2, n = problem_dims(r1, r2)
+        args = (m_ort, q1, q2, n, int(r1["n_faces"]), int(r2["n_faces"]), int(r1["type"]) == POLYTOPE,
+                int(r2["type"]) == POLYTOPE)
+        f0 = flop_model(*args, 0)
+        fit = flop_model(*args, 1) - f0
+        total += cnt[k] * f0 + its[k] * fit
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def cpu_baseline(n_target_seconds=12.0, threads=None, seed=1234):
+    """The oracle (C port of the reference path, FD gradient as in the reference) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    threads = threads or os.cpu_count() or 1
+    (rec, A, b), i1, i2, p1, p2 = make_batch(1 << 16, seed)
+    t = time.perf_counter()
+    O.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=O.GRAD_FD, threads=threads)
+    rate = (1 << 16) / (time.perf_counter() - t)
+    n = int(min(max(rate * n_target_seconds, 1 << 16), 1 << 24))
+    (rec, A, b), i1, i2, p1, p2 = make_batch(n, seed)
+    t = time.perf_counter()
+    r = O.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=O.GRAD_FD, threads=threads)
+    dt = time.perf_counter() - t
+    assert int((r["status"] != 0).sum()) == 0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n} pairs of the config-4 batch (seed {seed}), oracle/dcol_oracle.c with the reference's "
+                      f"13-evaluation finite-difference gradient, {threads} POSIX threads, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
+    itself is pure Python and cannot be compiled into oracle/_ref), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    threads = os.cpu_count() or 1
+    n = args.ref_pairs
+    (rec, A, b), i1, i2, p1, p2 = make_batch(n, 1234)
+    for _ in range(args.warmup):
+        O.solve_batch(rec, A, b, i1[:n // 8], i2[:n // 8], p1[:n // 8], p2[:n // 8], grad_mode=O.GRAD_FD, threads=threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        O.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=O.GRAD_FD, threads=threads)
+    dt = (time.perf_counter() - t) / args.steps
+    v = n / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": n, "note": "bounded sample of the same workload"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n} pairs per step, oracle/dcol_oracle.c (C port of the NumPy reference, FD "
+                                       f"gradient), {threads} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=1 << 23, help="pairs per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-pairs", type=int, default=1 << 21, help="pairs per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import dcol_trajectory_optimization_b200 as d
+    from dcol_trajectory_optimization_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    B = args.pairs
+
+    (rec, A, b), i1, i2, p1, p2 = make_batch(B, 1234 + rank)
+    eng = d.ProximityEngine((rec, A, b), device=local_rank)
+    fp64_peak = d.measure_fp64_peak(local_rank)
+    d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
+    plan = eng.plan(i1, i2)
+    flat, out = parallel.alloc_packed(B, dev)
+    gathered = torch.empty((world, flat.numel()), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        eng.solve(plan, d1, d2, out=out)
+        if world > 1:
+            parallel.all_gather_packed(flat, B, world, out=gathered)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = time.time()
+    ev[0].record()
+    for s in range(args.steps):
+        kev[s][0].record()
+        eng.solve(plan, d1, d2, out=out)
+        kev[s][1].record()
+        if world > 1:
+            parallel.all_gather_packed(flat, B, world, out=gathered)
+    ev[1].record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=dev)
+    kms = torch.tensor([sum(a.elapsed_time(bb) for a, bb in kev) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = B * world / (ms_per_step * 1e-3)
+
+    iters = out.iters.cpu().numpy()
+    n_fail = int((out.status != 0).sum())
+    flops = flop_model_total(rec, i1, i2, iters)
+    kernel_ms = float(kms)
+    achieved = flops / (kernel_ms * 1e-3)
+    bytes_alg = B * (96 + 4 + 136)   # poses + perm in, record out
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # ---- end to end through the host entry point of the C ABI (pinned host buffers) ----
+    e2e = None
+    if not args.no_e2e:
+        Be = B
+        hi1, hi2 = d.pinned_empty(Be, np.int32), d.pinned_empty(Be, np.int32)
+        hp1, hp2 = d.pinned_empty((Be, 6)), d.pinned_empty((Be, 6))
+        hi1[:], hi2[:], hp1[:], hp2[:] = i1, i2, p1, p2
+        hout = d.BatchResult(alpha=d.pinned_empty(Be), contact=d.pinned_empty((Be, 3)), grad=d.pinned_empty((Be, 12)),
+                             iters=d.pinned_empty(Be, np.int32), status=d.pinned_empty(Be, np.int32))
+        for _ in range(2):
+            eng.solve_host(hi1, hi2, hp1, hp2, out=hout)
+        barrier()
+        t = time.perf_counter()
+        n_e2e = max(3, args.steps // 2)
+        for _ in range(n_e2e):
+            eng.solve_host(hi1, hi2, hp1, hp2, out=hout)
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert np.array_equal(hout.iters, iters)
+        e2e = {"value": Be * world / float(dt), "unit": UNIT, "h2d_bytes_per_step": Be * (48 + 48 + 4 + 4),
+               "d2h_bytes_per_step": Be * (8 + 24 + 96 + 4 + 4), "ms_per_step": float(dt) * 1e3,
+               "api": "dcol_proximity_batch_host (ProximityEngine.solve_host), page-locked NumPy buffers, "
+                      "includes the per-chunk plan (counting sort)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "type_pairs": plan.n_groups,
+                       "mean_pdip_iters": float(iters.mean()), "failed_pairs": n_fail,
+                       "l2": "inputs larger than L2 (805 MB of poses per step at the default size)",
+                       "collective": "one all_gather_into_tensor of 136 B/pair records per step" if world > 1 else "none",
+                       "parallelism": f"batch sharded over {world} GPU(s), one process per GPU"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": args.steps * plan.n_launches,
+            "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "kernel": "dcol::pair_kernel<P1,P2> (40 specialisations, one launch each per step)",
+                         "kernel_ms_per_step": kernel_ms, "model_flops_per_pair": flops / B,
+                         "peak_source": "dcol_measure_fp64_peak in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "hbm": {"achieved": bytes_alg / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bytes_alg / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "bytes_per_pair": 236}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,578 @@
+/*
+ * dcol_api.cu — the C ABI of include/dcol.h: shape tables, plans (grouping a batch by shape pair
+ * with a device counting sort), the batched solve on device or host buffers, the single-pair debug
+ * trace and the FP64 peak probe.  No torch types, no CPU fallback: without a CUDA device every
+ * compute entry point fails with DCOL_E_NOGPU.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dcol_kernels.cuh"
+
+using namespace dcol;
+
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what)
+{
+    g_last_error = what;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* where)
+{
+    g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define DCOL_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);    \
+    } while (0)
+
+struct Group {
+    int32_t i1, i2;
+    int64_t first, count;
+    bool supported;
+};
+
+/* scratch of the host-buffer entry point, cached per table and grown on demand */
+struct HostScratch {
+    int64_t cap = 0;
+    int32_t *idx1 = nullptr, *idx2 = nullptr, *iters = nullptr, *status = nullptr;
+    double *pose1 = nullptr, *pose2 = nullptr, *alpha = nullptr, *contact = nullptr, *grad = nullptr;
+    void release()
+    {
+        cudaFree(idx1); cudaFree(idx2); cudaFree(iters); cudaFree(status);
+        cudaFree(pose1); cudaFree(pose2); cudaFree(alpha); cudaFree(contact); cudaFree(grad);
+        *this = HostScratch();
+    }
+};
+
+} /* namespace */
+
+struct dcol_shape_table {
+    int device;
+    std::vector<dcol_shape> shapes;
+    std::vector<int> cls;
+    std::vector<double> A, b;
+    /* host entry point state */
+    std::mutex mu;
+    HostScratch scratch[2];
+    cudaStream_t streams[3] = { nullptr, nullptr, nullptr }; /* h2d, compute, d2h */
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+};
+
+struct dcol_plan {
+    const dcol_shape_table* table;
+    int64_t B;
+    int32_t* d_perm;
+    std::vector<Group> groups;
+    int32_t n_launches;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* plan kernels: counting sort of the pairs by key = idx1 * n_shapes + idx2                     */
+namespace {
+
+constexpr int kPlanThreads = 256;
+constexpr int kPlanTile = 4096;    /* consecutive pairs per CTA            */
+constexpr int kPlanSmemKeys = 4096; /* keys a CTA can privatise in shared memory */
+
+__global__ void plan_histogram(const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2, int64_t B,
+                               int32_t n_shapes, int32_t n_keys, int32_t* __restrict__ counts, int32_t* __restrict__ err)
+{
+    __shared__ int32_t local[kPlanSmemKeys];
+    const bool priv = n_keys <= kPlanSmemKeys;
+    if (priv) {
+        for (int i = threadIdx.x; i < n_keys; i += kPlanThreads) local[i] = 0;
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * kPlanTile;
+    for (int o = threadIdx.x; o < kPlanTile; o += kPlanThreads) {
+        const int64_t k = base + o;
+        if (k >= B) break;
+        const int32_t a = idx1[k], c = idx2[k];
+        if (a < 0 || a >= n_shapes || c < 0 || c >= n_shapes) {
+            *err = 1;
+            continue;
+        }
+        const int32_t key = a * n_shapes + c;
+        if (priv) atomicAdd(&local[key], 1);
+        else atomicAdd(&counts[key], 1);
+    }
+    if (priv) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_keys; i += kPlanThreads)
+            if (local[i]) atomicAdd(&counts[i], local[i]);
+    }
+}
+
+/* cursor[key] starts at the group's first slot; every CTA reserves a contiguous range per key, so
+ * pairs stay in increasing order inside a CTA's tile and nearly so across the group (coalescing) */
+__global__ void plan_scatter(const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2, int64_t B,
+                             int32_t n_shapes, int32_t n_keys, int32_t* __restrict__ cursor, int32_t* __restrict__ perm)
+{
+    __shared__ int32_t local[kPlanSmemKeys];
+    __shared__ int32_t base_of[kPlanSmemKeys];
+    const bool priv = n_keys <= kPlanSmemKeys;
+    const int64_t base = (int64_t)blockIdx.x * kPlanTile;
+    if (priv) {
+        for (int i = threadIdx.x; i < n_keys; i += kPlanThreads) local[i] = 0;
+        __syncthreads();
+        for (int o = threadIdx.x; o < kPlanTile; o += kPlanThreads) {
+            const int64_t k = base + o;
+            if (k >= B) break;
+            const int32_t a = idx1[k], c = idx2[k];
+            if (a < 0 || a >= n_shapes || c < 0 || c >= n_shapes) continue;
+            atomicAdd(&local[a * n_shapes + c], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_keys; i += kPlanThreads) {
+            base_of[i] = local[i] ? atomicAdd(&cursor[i], local[i]) : 0;
+            local[i] = 0;
+        }
+        __syncthreads();
+    }
+    /* ordered inside the tile: thread-sequential chunks would need a scan; a shared-memory ticket is
+     * enough because the solve only needs every pair exactly once */
+    for (int o = threadIdx.x; o < kPlanTile; o += kPlanThreads) {
+        const int64_t k = base + o;
+        if (k >= B) break;
+        const int32_t a = idx1[k], c = idx2[k];
+        if (a < 0 || a >= n_shapes || c < 0 || c >= n_shapes) continue;
+        const int32_t key = a * n_shapes + c;
+        const int32_t pos = priv ? base_of[key] + atomicAdd(&local[key], 1) : atomicAdd(&cursor[key], 1);
+        perm[pos] = (int32_t)k;
+    }
+}
+
+/* pairs the reference cannot assemble (combine_problem_matrices.py:58-67 raises ValueError) */
+__global__ void fill_unsupported(BatchArgs b)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.count) return;
+    const int64_t k = b.perm ? (int64_t)b.perm[b.first + t] : b.first + t;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    b.status[k] = DCOL_STATUS_UNSUPPORTED;
+    b.iters[k] = 0;
+    b.alpha[k] = nan;
+    if (b.flags & DCOL_WANT_CONTACT)
+        for (int j = 0; j < 3; ++j) b.contact[3 * k + j] = nan;
+    if (b.flags & DCOL_WANT_GRAD)
+        for (int j = 0; j < 12; ++j) b.grad[12 * k + j] = nan;
+}
+
+/* FP64 FMA peak: 8 independent chains per thread, no memory traffic */
+__global__ void fp64_peak_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) out[0] = s; /* never true: keeps the chains alive */
+}
+
+cudaError_t launch_group(const dcol_shape_table* T, int32_t i1, int32_t i2, const BatchArgs& args, cudaStream_t stream)
+{
+    GroupLaunch g = { &T->shapes[i1], &T->shapes[i2], T->A.data(), T->b.data(), args };
+    const int c2 = T->cls[i2];
+    switch (T->cls[i1]) {
+    case CLS_POLY6: return launch_first_class<CLS_POLY6>(c2, g, stream);
+    case CLS_POLY8: return launch_first_class<CLS_POLY8>(c2, g, stream);
+    case CLS_POLYN: return launch_first_class<CLS_POLYN>(c2, g, stream);
+    case CLS_CAPSULE: return launch_first_class<CLS_CAPSULE>(c2, g, stream);
+    case CLS_CYLINDER: return launch_first_class<CLS_CYLINDER>(c2, g, stream);
+    case CLS_CONE: return launch_first_class<CLS_CONE>(c2, g, stream);
+    case CLS_SPHERE: return launch_first_class<CLS_SPHERE>(c2, g, stream);
+    case CLS_PGON5: return launch_first_class<CLS_PGON5>(c2, g, stream);
+    case CLS_PGONN: return launch_first_class<CLS_PGONN>(c2, g, stream);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(DCOL_E_NOGPU, "no CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(DCOL_E_ARG, "device ordinal out of range");
+    return 0;
+}
+
+} /* namespace */
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+const char* dcol_version(void) { return "dcol-b200 0.1 (abi 1, sm_100a)"; }
+const char* dcol_last_error(void) { return g_last_error.c_str(); }
+
+int dcol_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dcol_shape_table_create(const dcol_shape* shapes, int32_t n_shapes, const double* A, const double* b,
+                            int32_t n_faces, int device, dcol_shape_table** out)
+{
+    if (!shapes || !out || n_shapes <= 0 || n_faces < 0 || (n_faces > 0 && (!A || !b)))
+        return fail(DCOL_E_ARG, "dcol_shape_table_create: bad argument");
+    if (n_shapes > 1024) return fail(DCOL_E_ARG, "dcol_shape_table_create: at most 1024 shapes per table");
+    int rc = check_device(device);
+    if (rc) return rc;
+    dcol_shape_table* T = new dcol_shape_table();
+    T->device = device;
+    T->shapes.assign(shapes, shapes + n_shapes);
+    T->A.assign(A, A + 3 * (size_t)n_faces);
+    T->b.assign(b, b + (size_t)n_faces);
+    if (n_faces == 0) {
+        T->A.assign(3, 0.0);
+        T->b.assign(1, 0.0);
+    }
+    T->cls.resize(n_shapes);
+    for (int i = 0; i < n_shapes; ++i) {
+        const dcol_shape& s = T->shapes[i];
+        const int c = shape_class(s);
+        const bool faces = s.type == DCOL_POLYTOPE || s.type == DCOL_POLYGON;
+        if (c < 0 || (faces && (s.face_off < 0 || s.face_off + s.n_faces > n_faces))) {
+            delete T;
+            return fail(DCOL_E_SHAPE, "dcol_shape_table_create: malformed shape record");
+        }
+        T->cls[i] = c;
+    }
+    *out = T;
+    return 0;
+}
+
+void dcol_shape_table_destroy(dcol_shape_table* T)
+{
+    if (!T) return;
+    cudaSetDevice(T->device);
+    for (int i = 0; i < 2; ++i) {
+        T->scratch[i].release();
+        if (T->ev_in[i]) cudaEventDestroy(T->ev_in[i]);
+        if (T->ev_done[i]) cudaEventDestroy(T->ev_done[i]);
+        if (T->ev_out[i]) cudaEventDestroy(T->ev_out[i]);
+    }
+    for (int i = 0; i < 3; ++i)
+        if (T->streams[i]) cudaStreamDestroy(T->streams[i]);
+    delete T;
+}
+
+int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int32_t* d_idx2, int64_t B, void* stream_,
+                     dcol_plan** out)
+{
+    if (!T || !out || B < 0 || (B > 0 && (!d_idx1 || !d_idx2))) return fail(DCOL_E_ARG, "dcol_plan_create: bad argument");
+    if (B > 0x7fffffffLL) return fail(DCOL_E_ARG, "dcol_plan_create: at most 2^31-1 pairs per plan");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCOL_CUDA(cudaSetDevice(T->device));
+    dcol_plan* P = new dcol_plan();
+    P->table = T;
+    P->B = B;
+    P->d_perm = nullptr;
+    P->n_launches = 0;
+    if (B == 0) {
+        *out = P;
+        return 0;
+    }
+    const int32_t ns = (int32_t)T->shapes.size();
+    const int32_t nk = ns * ns;
+    int32_t* d_counts = nullptr;
+    cudaError_t e = cudaMalloc(&d_counts, sizeof(int32_t) * ((size_t)nk + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_perm, sizeof(int32_t) * (size_t)B);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * ((size_t)nk + 1), stream);
+    const unsigned blocks = (unsigned)((B + kPlanTile - 1) / kPlanTile);
+    std::vector<int32_t> counts((size_t)nk + 1);
+    if (e == cudaSuccess) {
+        plan_histogram<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, d_counts, d_counts + nk);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), d_counts, sizeof(int32_t) * ((size_t)nk + 1), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess || counts[nk] != 0) {
+        cudaFree(d_counts);
+        cudaFree(P->d_perm);
+        delete P;
+        if (e != cudaSuccess) return fail_cuda(e, "dcol_plan_create");
+        return fail(DCOL_E_INDEX, "dcol_plan_create: shape index out of range");
+    }
+    std::vector<int32_t> cursor((size_t)nk, 0);
+    int64_t off = 0;
+    for (int32_t key = 0; key < nk; ++key) {
+        cursor[key] = (int32_t)off;
+        if (counts[key] == 0) continue;
+        Group g;
+        g.i1 = key / ns;
+        g.i2 = key % ns;
+        g.first = off;
+        g.count = counts[key];
+        g.supported = class_pair_supported(T->cls[g.i1], T->cls[g.i2]);
+        P->groups.push_back(g);
+        off += counts[key];
+    }
+    P->n_launches = (int32_t)P->groups.size();
+    e = cudaMemcpyAsync(d_counts, cursor.data(), sizeof(int32_t) * (size_t)nk, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
+        plan_scatter<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, d_counts, P->d_perm);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream); /* cursor is host memory about to go away */
+    cudaFree(d_counts);
+    if (e != cudaSuccess) {
+        cudaFree(P->d_perm);
+        delete P;
+        return fail_cuda(e, "dcol_plan_create");
+    }
+    *out = P;
+    return 0;
+}
+
+void dcol_plan_destroy(dcol_plan* P)
+{
+    if (!P) return;
+    if (P->d_perm) {
+        cudaSetDevice(P->table->device);
+        cudaFree(P->d_perm);
+    }
+    delete P;
+}
+int64_t dcol_plan_size(const dcol_plan* P) { return P ? P->B : 0; }
+int32_t dcol_plan_n_groups(const dcol_plan* P) { return P ? (int32_t)P->groups.size() : 0; }
+int32_t dcol_plan_n_launches(const dcol_plan* P) { return P ? P->n_launches : 0; }
+
+int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
+                                int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact, double* d_grad,
+                                int32_t* d_iters, int32_t* d_status, void* stream_)
+{
+    if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null plan");
+    if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
+    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "unknown flag");
+    if (P->B == 0) return 0;
+    if (!d_pose1 || !d_pose2 || !d_alpha || !d_iters || !d_status || ((flags & DCOL_WANT_CONTACT) && !d_contact) ||
+        ((flags & DCOL_WANT_GRAD) && !d_grad))
+        return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null buffer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCOL_CUDA(cudaSetDevice(P->table->device));
+    for (const Group& g : P->groups) {
+        BatchArgs a = { P->d_perm, g.first, g.count, d_pose1, d_pose2, tol, max_iter, flags,
+                        d_alpha, d_contact, d_grad, d_iters, d_status, nullptr };
+        if (!g.supported) {
+            fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, stream>>>(a);
+            DCOL_CUDA(cudaGetLastError());
+            continue;
+        }
+        cudaError_t e = launch_group(P->table, g.i1, g.i2, a, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "pair_kernel launch");
+    }
+    return 0;
+}
+
+/* Host buffers: the batch is cut into chunks that flow through three streams (copy in, plan + solve,
+ * copy out) with two sets of device scratch, so PCIe traffic in both directions overlaps the solve. */
+int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, const int32_t* idx2, const double* pose1,
+                              const double* pose2, int64_t B, double tol, int32_t max_iter, uint32_t flags,
+                              double* alpha, double* contact, double* grad, int32_t* iters, int32_t* status)
+{
+    dcol_shape_table* T = const_cast<dcol_shape_table*>(T_);
+    if (!T || B < 0) return fail(DCOL_E_ARG, "dcol_proximity_batch_host: bad argument");
+    if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
+    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "unknown flag");
+    if (B == 0) return 0;
+    if (!idx1 || !idx2 || !pose1 || !pose2 || !alpha || !iters || !status || ((flags & DCOL_WANT_CONTACT) && !contact) ||
+        ((flags & DCOL_WANT_GRAD) && !grad))
+        return fail(DCOL_E_ARG, "dcol_proximity_batch_host: null buffer");
+    std::lock_guard<std::mutex> lock(T->mu);
+    DCOL_CUDA(cudaSetDevice(T->device));
+    for (int i = 0; i < 3; ++i)
+        if (!T->streams[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!T->ev_in[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_in[i], cudaEventDisableTiming));
+        if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
+        if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
+    }
+    const int64_t kChunk = 1 << 20;
+    const int64_t chunk = std::min<int64_t>(B, kChunk);
+    for (int i = 0; i < 2; ++i) {
+        HostScratch& S = T->scratch[i];
+        if (S.cap >= chunk) continue;
+        S.release();
+        DCOL_CUDA(cudaMalloc(&S.idx1, sizeof(int32_t) * chunk));
+        DCOL_CUDA(cudaMalloc(&S.idx2, sizeof(int32_t) * chunk));
+        DCOL_CUDA(cudaMalloc(&S.iters, sizeof(int32_t) * chunk));
+        DCOL_CUDA(cudaMalloc(&S.status, sizeof(int32_t) * chunk));
+        DCOL_CUDA(cudaMalloc(&S.pose1, sizeof(double) * 6 * chunk));
+        DCOL_CUDA(cudaMalloc(&S.pose2, sizeof(double) * 6 * chunk));
+        DCOL_CUDA(cudaMalloc(&S.alpha, sizeof(double) * chunk));
+        DCOL_CUDA(cudaMalloc(&S.contact, sizeof(double) * 3 * chunk));
+        DCOL_CUDA(cudaMalloc(&S.grad, sizeof(double) * 12 * chunk));
+        S.cap = chunk;
+    }
+    cudaStream_t s_in = T->streams[0], s_run = T->streams[1], s_out = T->streams[2];
+    int rc = 0;
+    dcol_plan* plans[2] = { nullptr, nullptr };
+    int64_t n_chunks = (B + chunk - 1) / chunk;
+    for (int64_t ci = 0; ci < n_chunks && rc == 0; ++ci) {
+        const int slot = (int)(ci & 1);
+        HostScratch& S = T->scratch[slot];
+        const int64_t k0 = ci * chunk, n = std::min(chunk, B - k0);
+        if (ci >= 2) {
+            /* the slot's previous outputs must have left the device, its inputs must have been consumed */
+            DCOL_CUDA(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));
+            DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));
+        }
+        DCOL_CUDA(cudaMemcpyAsync(S.idx1, idx1 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA(cudaMemcpyAsync(S.idx2, idx2 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA(cudaMemcpyAsync(S.pose1, pose1 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA(cudaMemcpyAsync(S.pose2, pose2 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA(cudaEventRecord(T->ev_in[slot], s_in));
+        DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
+        /* the slot's previous plan: its solve finished before the last plan_create returned (same stream) */
+        dcol_plan_destroy(plans[slot]);
+        plans[slot] = nullptr;
+        rc = dcol_plan_create(T, S.idx1, S.idx2, n, s_run, &plans[slot]);
+        if (rc) break;
+        dcol_plan* P = plans[slot];
+        rc = dcol_proximity_batch_device(P, S.pose1, S.pose2, tol, max_iter, flags, S.alpha, S.contact, S.grad, S.iters,
+                                         S.status, s_run);
+        cudaError_t e = cudaEventRecord(T->ev_done[slot], s_run);
+        if (rc == 0 && e == cudaSuccess) e = cudaStreamWaitEvent(s_out, T->ev_done[slot], 0);
+        if (rc == 0 && e == cudaSuccess) e = cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out);
+        if (rc == 0 && e == cudaSuccess) e = cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out);
+        if (rc == 0 && e == cudaSuccess) e = cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out);
+        if (rc == 0 && e == cudaSuccess && (flags & DCOL_WANT_CONTACT))
+            e = cudaMemcpyAsync(contact + 3 * k0, S.contact, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s_out);
+        if (rc == 0 && e == cudaSuccess && (flags & DCOL_WANT_GRAD))
+            e = cudaMemcpyAsync(grad + 12 * k0, S.grad, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cudaEventRecord(T->ev_out[slot], s_out);
+        if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_batch_host");
+    }
+    cudaError_t e = cudaStreamSynchronize(s_out);
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_run);
+    dcol_plan_destroy(plans[0]);
+    dcol_plan_destroy(plans[1]);
+    if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_batch_host");
+    return rc;
+}
+
+/* page-locked host memory, so that the host entry point's copies run asynchronously at PCIe rate */
+int dcol_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return fail(DCOL_E_ARG, "null argument");
+    int rc = check_device(0);
+    if (rc) return rc;
+    DCOL_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+void dcol_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int dcol_debug_trace_pair(const dcol_shape_table* T, int32_t idx1, int32_t idx2, const double* pose1, const double* pose2,
+                          double tol, double* alpha, double* x, double* s, double* z, int32_t* n, int32_t* m,
+                          int32_t* iters, int32_t* status, double* mu_trace)
+{
+    if (!T || !pose1 || !pose2 || !alpha || !x || !s || !z || !n || !m || !iters || !status || !mu_trace)
+        return fail(DCOL_E_ARG, "dcol_debug_trace_pair: null argument");
+    const int32_t ns = (int32_t)T->shapes.size();
+    if (idx1 < 0 || idx1 >= ns || idx2 < 0 || idx2 >= ns) return fail(DCOL_E_INDEX, "shape index out of range");
+    DCOL_CUDA(cudaSetDevice(T->device));
+    const double nan = __builtin_nan("");
+    *alpha = nan; *n = 0; *m = 0; *iters = 0;
+    for (int i = 0; i <= DCOL_MAX_ITER; ++i) mu_trace[i] = nan;
+    if (!class_pair_supported(T->cls[idx1], T->cls[idx2])) {
+        *status = DCOL_STATUS_UNSUPPORTED;
+        return 0;
+    }
+    struct Dev {
+        double pose[12], alpha;
+        int32_t iters, status;
+        TraceOut tr;
+    };
+    Dev* d = nullptr;
+    DCOL_CUDA(cudaMalloc(&d, sizeof(Dev)));
+    Dev* h = new Dev();
+    memcpy(h->pose, pose1, 6 * sizeof(double));
+    memcpy(h->pose + 6, pose2, 6 * sizeof(double));
+    cudaError_t e = cudaMemcpy(d, h, sizeof(Dev), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        BatchArgs a = { nullptr, 0, 1, d->pose, d->pose + 6, tol, DCOL_MAX_ITER, 0u,
+                        &d->alpha, nullptr, nullptr, &d->iters, &d->status, &d->tr };
+        e = launch_group(T, idx1, idx2, a, 0);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(Dev), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail_cuda(e, "dcol_debug_trace_pair");
+    }
+    *alpha = h->alpha; *iters = h->iters; *status = h->status; *n = h->tr.n; *m = h->tr.m;
+    memcpy(x, h->tr.x, sizeof(double) * 8);
+    memcpy(s, h->tr.s, sizeof(double) * h->tr.m);
+    memcpy(z, h->tr.z, sizeof(double) * h->tr.m);
+    memcpy(mu_trace, h->tr.mu, sizeof(double) * (DCOL_MAX_ITER + 1));
+    delete h;
+    return 0;
+}
+
+int dcol_measure_fp64_peak(int device, double* flops_per_s)
+{
+    if (!flops_per_s) return fail(DCOL_E_ARG, "null argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DCOL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DCOL_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    DCOL_CUDA(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    DCOL_CUDA(cudaEventCreate(&e0));
+    DCOL_CUDA(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, 0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(e1, 0);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return fail_cuda(e, "fp64_peak_kernel");
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *flops_per_s = best;
+    return 0;
+}
+
+} /* extern "C" */

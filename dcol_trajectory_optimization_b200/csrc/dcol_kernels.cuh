@@ -1,0 +1,168 @@
+/*
+ * dcol_kernels.cuh — the batched proximity kernel: one thread owns one pair and runs the whole
+ * solve (dcol_solver.cuh) in registers.  One launch covers one GROUP of the plan: all pairs that
+ * share the same two shape records, so every shape constant is a kernel parameter (constant bank,
+ * warp-uniform) and a thread reads only its two poses (96 B) and writes its results (<= 136 B).
+ *
+ * Replaces the per-pair Python call chain proximity_gradient -> problem_matrices x2 ->
+ * combine_problem_matrices -> solve_lp_pdip -> obj_val_grad
+ * (proximity/proximity_gradient.py:91-138) evaluated in loops at
+ * systems/cluttered_hallway_quadrotor.py:131-133,155 and friends.
+ */
+#ifndef DCOL_KERNELS_CUH_
+#define DCOL_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+
+#include "dcol_classes.cuh"
+
+namespace dcol {
+
+constexpr int kThreads = 64; /* threads per CTA: register-heavy FP64 code, 4+ CTAs per SM */
+
+/* everything of a launch that does not depend on the specialisation */
+struct BatchArgs {
+    const int32_t* perm; /* plan order -> pair index, or null for the identity */
+    int64_t first, count;
+    const double* pose1; /* [B][6] rows (r, p) */
+    const double* pose2;
+    double tol;
+    int32_t max_iter;
+    uint32_t flags;
+    double* alpha;   /* [B]      */
+    double* contact; /* [B][3]   */
+    double* grad;    /* [B][12]  */
+    int32_t* iters;  /* [B]      */
+    int32_t* status; /* [B]      */
+    struct TraceOut* trace; /* debug entry point only (count == 1): mu trace and world-frame (x, s, z) */
+};
+
+/* one pair with the mu trace and the world-frame (x, s, z): the debug entry point */
+struct TraceOut {
+    double x[8], s[2 * DCOL_MAX_FACES + 8], z[2 * DCOL_MAX_FACES + 8], mu[DCOL_MAX_ITER + 1];
+    int32_t n, m;
+};
+
+template <class P1, class P2>
+struct GroupArgs {
+    typename P1::Const c1;
+    typename P2::Const c2;
+    BatchArgs b;
+};
+
+template <class P1, class P2>
+__global__ void __launch_bounds__(kThreads) pair_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
+{
+    typedef Solver<P1, P2> S;
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= a.b.count) return;
+    const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + t] : a.b.first + t;
+
+    double pose1[6], pose2[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
+        pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
+    }
+    S sv;
+    PairResult<S::N> res;
+    const bool want_grad = (a.b.flags & DCOL_WANT_GRAD) != 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    Trace tr = { nullptr };
+    if (a.b.trace) {
+        tr.mu = a.b.trace->mu;
+        for (int i = 0; i <= DCOL_MAX_ITER; ++i) tr.mu[i] = nan;
+    }
+    const int st = sv.solve(a.c1, a.c2, pose1, pose2, a.b.tol, a.b.max_iter, want_grad, res, &tr);
+    a.b.status[k] = st;
+    a.b.iters[k] = res.iters;
+    a.b.alpha[k] = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
+    if (a.b.flags & DCOL_WANT_CONTACT) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = st == DCOL_STATUS_OK ? sv.x[j] : nan; /* proximity.py:52 */
+    }
+    if (want_grad) {
+        double g[12];
+        if (st == DCOL_STATUS_OK) {
+            sv.gradient(a.c1, a.c2, pose1, pose2, g);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) g[j] = nan;
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+    }
+    if (a.b.trace) {
+        TraceOut* out = a.b.trace;
+        out->n = S::N;
+        for (int j = 0; j < 8; ++j) out->x[j] = nan;
+        if (st == DCOL_STATUS_OK) {
+#pragma unroll
+            for (int j = 0; j < S::N; ++j) out->x[j] = sv.x[j];
+        }
+        out->m = st == DCOL_STATUS_OK ? sv.export_sz(a.c1, a.c2, out->s, out->z) : 0;
+    }
+}
+
+/* host-side description of one launch */
+struct GroupLaunch {
+    const dcol_shape* s1; /* host copies of the two shape records */
+    const dcol_shape* s2;
+    const double* A;      /* host copies of the packed faces      */
+    const double* b;
+    BatchArgs args;
+};
+
+template <int C1, int C2>
+cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
+{
+    typedef typename ClassPrim<C1>::type P1;
+    typedef typename ClassPrim<C2>::type P2;
+    GroupArgs<P1, P2> a;
+    fill_const(*g.s1, g.A, g.b, a.c1);
+    fill_const(*g.s2, g.A, g.b, a.c2);
+    a.b = g.args;
+    if (g.args.count <= 0) return cudaSuccess;
+    const int64_t blocks = (g.args.count + kThreads - 1) / kThreads;
+    pair_kernel<P1, P2><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+/* one translation unit per first class (dcol_inst_*.cu) defines these */
+template <int C1>
+cudaError_t launch_first_class(int c2, const GroupLaunch& g, cudaStream_t stream);
+template <> cudaError_t launch_first_class<CLS_POLY6>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_POLY8>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_POLYN>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_CAPSULE>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_CYLINDER>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_CONE>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_SPHERE>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_PGON5>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_PGONN>(int, const GroupLaunch&, cudaStream_t);
+
+#define DCOL_DEFINE_FIRST_CLASS(C1)                                                              \
+    namespace dcol {                                                                             \
+    namespace {                                                                                  \
+    struct LaunchFn_##C1 {                                                                       \
+        const GroupLaunch* g;                                                                    \
+        cudaStream_t stream;                                                                     \
+        cudaError_t err;                                                                         \
+        template <int A1, int A2>                                                                \
+        void operator()()                                                                        \
+        {                                                                                        \
+            err = launch_pair<A1, A2>(*g, stream);                                               \
+        }                                                                                        \
+    };                                                                                           \
+    }                                                                                            \
+    template <>                                                                                  \
+    cudaError_t launch_first_class<C1>(int c2, const GroupLaunch& g, cudaStream_t stream)        \
+    {                                                                                            \
+        LaunchFn_##C1 f = { &g, stream, cudaSuccess };                                           \
+        if (!dispatch_class2<C1>(c2, f)) return cudaErrorInvalidValue;                           \
+        return f.err;                                                                            \
+    }                                                                                            \
+    }
+
+} /* namespace dcol */
+#endif /* DCOL_KERNELS_CUH_ */

@@ -1,0 +1,1066 @@
+/*
+ * dcol_solver.cuh — one (primitive, primitive) proximity solve + pose gradient, owned by ONE thread.
+ *
+ * The whole fixed-cap primal-dual interior-point loop of the reference
+ *     proximity/pdip.py:373-470 (solve_lp_pdip), :291-332 (initialize), :237-287 (bring2cone)
+ *     proximity/NT/NT_scaling.py:340-463 (Nesterov-Todd scaling)
+ *     primitives/problem_matrices.py:4-364, primitives/combine_problem_matrices.py:3-70 (assembly)
+ *     proximity/proximity_gradient.py:50-88 (gradient of the frozen-(x,z) Lagrangian)
+ * runs in registers, in FP64, specialised at compile time on the pair's kinds and face counts.
+ *
+ * It is the same algorithm, iterate for iterate (same initial point incl. the diag-only
+ * triangular solve, same mu-only stopping test, same Mehrotra predictor / corrector, same
+ * un-damped affine step and 0.99-damped final step, same 50-iteration cap) but NOT the same
+ * arithmetic layout.  What is different, and why it is exact-arithmetic equivalent:
+ *
+ *  1. Body-frame constraint rows.  Every primitive's block of G x - h equals a CONSTANT matrix
+ *     applied to the local vector (Q'^T (x - r'), alpha, extras): the pose enters only through
+ *     that affine map.  So G is never stored: its coefficients are warp-uniform shape constants
+ *     (kernel parameters -> constant bank operands), a thread keeps only Q' and r' of each
+ *     primitive, and Gram matrices / adjoint products are accumulated in the local frame and
+ *     rotated once.  Second-order-cone rows of ball-like primitives are carried in body-frame
+ *     components (a rotation of the cone's vector part commutes with every cone operation).
+ *  2. Scaled-space Newton step.  With lambda = W z = W^-1 s, the directions are carried as
+ *     ds~ = W^-1 ds and dz~ = W dz.  Both line searches then run against lambda (W is an
+ *     automorphism of the cone), the orthant needs one rsqrt per row per iteration instead of
+ *     ~8 divisions/square roots, and the centring ratio uses <ds, dz> = <ds~, dz~>.
+ *  3. W^-1 of a second-order cone in closed form (1/eta) J Wbar J, no Cholesky of W.
+ *
+ * Rounding therefore differs from NumPy at the 1e-16 level per operation; SURVEY.md section 0
+ * measured that such noise moves alpha by <= 2e-14 and never flips an iteration count.
+ *
+ * Compiles as CUDA device code and as plain C++ (tests build a host twin of this header to
+ * debug the algorithm against the oracle without a GPU; the product never runs it on the CPU).
+ */
+#ifndef DCOL_SOLVER_CUH_
+#define DCOL_SOLVER_CUH_
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/dcol.h"
+
+#if defined(__CUDACC__)
+#define DCOL_HD __host__ __device__ __forceinline__
+#define DCOL_UNROLL _Pragma("unroll")
+#define DCOL_UNROLL_ROWS _Pragma("unroll (P::dyn ? 1 : 64)")
+#else
+#define DCOL_HD inline __attribute__((always_inline))
+#define DCOL_UNROLL
+#define DCOL_UNROLL_ROWS
+#endif
+
+namespace dcol {
+
+/* ---------------------------------------------------------------------------------------- */
+/* scalar helpers                                                                            */
+
+DCOL_HD double rsqrt_(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+DCOL_HD double rcp_(double x) { return 1.0 / x; }
+DCOL_HD double max_(double a, double b) { return (b > a) ? b : a; } /* Python max(a, b): keeps a on NaN */
+DCOL_HD double min_(double a, double b) { return (b < a) ? b : a; }
+/* 0 if x is finite, NaN otherwise (x * 0 is NaN for inf and NaN) */
+DCOL_HD double nonfinite_probe(double x) { return x * 0.0; }
+
+/* primitives/problem_matrices.py:213-251: direction cosine matrix of a modified Rodrigues vector,
+ * Q = I + (8 S^2 + 4 (1 - |p|^2) S) / (1 + |p|^2)^2 with S = [p x] */
+DCOL_HD void dcm_from_mrp(const double p[3], double Q[3][3])
+{
+    const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    const double t = 1.0 + pp;
+    const double iden = 1.0 / (t * t);
+    const double k8 = 8.0 * iden, k4 = 4.0 * (1.0 - pp) * iden;
+    Q[0][0] = 1.0 - k8 * (p[1] * p[1] + p[2] * p[2]);
+    Q[1][1] = 1.0 - k8 * (p[0] * p[0] + p[2] * p[2]);
+    Q[2][2] = 1.0 - k8 * (p[0] * p[0] + p[1] * p[1]);
+    Q[0][1] = k8 * p[0] * p[1] - k4 * p[2];
+    Q[1][0] = k8 * p[0] * p[1] + k4 * p[2];
+    Q[0][2] = k8 * p[0] * p[2] + k4 * p[1];
+    Q[2][0] = k8 * p[0] * p[2] - k4 * p[1];
+    Q[1][2] = k8 * p[1] * p[2] - k4 * p[0];
+    Q[2][1] = k8 * p[1] * p[2] + k4 * p[0];
+}
+
+/* <M, dQ/dp_k> for k = 0..2, with dQ_k = (dN_k - (Q - I) dD_k) / D, N = 8 S^2 + 4 (1-pp) S,
+ * D = (1+pp)^2.  (Analytic replacement for the reference's finite differences through
+ * dcm_from_mrp, proximity_gradient.py:80-86.) */
+DCOL_HD void dcm_derivative_contract(const double p[3], const double Q[3][3], const double M[3][3], double out[3])
+{
+    const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    const double t = 1.0 + pp, iD = 1.0 / (t * t);
+    const double S[3][3] = { { 0.0, -p[2], p[1] }, { p[2], 0.0, -p[0] }, { -p[1], p[0], 0.0 } };
+    DCOL_UNROLL
+    for (int k = 0; k < 3; ++k) {
+        /* S_k = [e_k x]:  S_k[c][a] = 1, S_k[a][c] = -1 with a = k+1, c = k+2 (mod 3) */
+        const int a = (k + 1) % 3, c = (k + 2) % 3;
+        const double dD = 4.0 * t * p[k];
+        double acc = 0.0;
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            DCOL_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                /* (S_k S)[i][j] = sum_l S_k[i][l] S[l][j];  (S S_k)[i][j] = sum_l S[i][l] S_k[l][j] */
+                double sks = 0.0, ssk = 0.0, skij = 0.0;
+                if (i == c) sks = S[a][j];
+                if (i == a) sks = -S[c][j];
+                if (j == a) ssk = S[i][c];
+                if (j == c) ssk = -S[i][a];
+                if (i == c && j == a) skij = 1.0;
+                if (i == a && j == c) skij = -1.0;
+                const double dN = 8.0 * (sks + ssk) - 8.0 * p[k] * S[i][j] + 4.0 * (1.0 - pp) * skij;
+                const double QmI = Q[i][j] - (i == j ? 1.0 : 0.0);
+                acc += M[i][j] * ((dN - QmI * dD) * iD);
+            }
+        }
+        out[k] = acc;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* shape constants: warp-uniform, passed by value as kernel parameters                       */
+
+template <int FMAX>
+struct ShapeConst {
+    double R, L, H, tanb;   /* tanb = tan(beta)                       */
+    double r_off[3];        /* body-frame origin offset               */
+    double Q_off[3][3];     /* body-frame rotation offset             */
+    int32_t nf, pad;        /* faces actually present                 */
+    double A[FMAX > 0 ? FMAX : 1][3];
+    double b[FMAX > 0 ? FMAX : 1];
+};
+
+/* ---------------------------------------------------------------------------------------- */
+/* primitive kinds.  Local variables of a primitive: xh = (y0, y1, y2, alpha, e0, e1) with     */
+/* y = Q'^T (x - r') and e its own extra decision variables.  In these variables every row of  */
+/* the primitive's block of G x - h has constant coefficients:                                 */
+/*   polytope  face i   :  A_i . y - b_i alpha                 problem_matrices.py:181-209     */
+/*   cone      orthant  :  y0 - (H/4) alpha                    problem_matrices.py:125-148     */
+/*             soc(3)   :  (-tanb y0 - (3/4) H tanb alpha, -y1, -y2)                           */
+/*   capsule   orthant  :  -(L/2) alpha +- e0                  problem_matrices.py:4-44        */
+/*             soc(4)   :  (-R alpha, -y0 + e0, -y1, -y2)                                      */
+/*   cylinder  capsule + :  -+ y0 - (L/2) alpha                problem_matrices.py:47-87       */
+/*   sphere    soc(4)   :  (-R alpha, -y)   (y in world axes)  problem_matrices.py:151-178     */
+/*   polygon   face i   :  -b_i alpha + A_i0 e0 + A_i1 e1      problem_matrices.py:90-120      */
+/*             soc(4)   :  (-R alpha, -y0 + e0, -y1 + e1, -y2)                                 */
+
+template <int KIND, int FC>
+struct Prim {
+    static constexpr int kind = KIND;
+    static constexpr bool has_faces = (KIND == DCOL_POLYTOPE || KIND == DCOL_POLYGON);
+    static constexpr bool dyn = has_faces && FC == 0;                       /* runtime face count      */
+    static constexpr int FMAX = has_faces ? (FC ? FC : DCOL_MAX_FACES) : 0; /* sized for               */
+    static constexpr int NO = has_faces ? FMAX : (KIND == DCOL_CONE ? 1 : KIND == DCOL_CAPSULE ? 2 : KIND == DCOL_CYLINDER ? 4 : 0);
+    static constexpr int NOA = NO > 0 ? NO : 1;                             /* array extent            */
+    static constexpr int Q = KIND == DCOL_POLYTOPE ? 0 : (KIND == DCOL_CONE ? 3 : 4);
+    static constexpr int QA = Q > 0 ? Q : 1;
+    static constexpr int NE = (KIND == DCOL_CAPSULE || KIND == DCOL_CYLINDER) ? 1 : (KIND == DCOL_POLYGON ? 2 : 0);
+    static constexpr int NL = 4 + NE;
+    static constexpr bool rot = KIND != DCOL_SPHERE;  /* the sphere's rows are written in world axes */
+    static constexpr bool ball = Q == 4;              /* soc rows (-R alpha, -y + E e)               */
+    typedef ShapeConst<FMAX> Const;
+    typedef Prim P;
+
+    double Qp[3][3]; /* Q' = Q(p) Q_offset                  */
+    double rp[3];    /* r' = r + Q(p) r_offset              */
+
+    DCOL_HD static int n_ort(const Const& c) { return dyn ? c.nf : NO; }
+
+    /* structural non-zero of orthant row i at local column j */
+    DCOL_HD static bool nz(int i, int j)
+    {
+        switch (KIND) {
+        case DCOL_POLYTOPE: return j < 4;
+        case DCOL_POLYGON: return j >= 3;
+        case DCOL_CONE: return j == 0 || j == 3;
+        case DCOL_CAPSULE: return j == 3 || j == 4;
+        case DCOL_CYLINDER: return i < 2 ? (j == 3 || j == 4) : (j == 0 || j == 3);
+        default: return false;
+        }
+    }
+    /* coefficient of orthant row i at local column j (where nz) */
+    DCOL_HD static double g(const Const& c, int i, int j)
+    {
+        switch (KIND) {
+        case DCOL_POLYTOPE: return j < 3 ? c.A[i][j] : -c.b[i];
+        case DCOL_POLYGON: return j == 3 ? -c.b[i] : c.A[i][j - 4];
+        case DCOL_CONE: return j == 0 ? 1.0 : -0.25 * c.H;
+        case DCOL_CAPSULE: return j == 3 ? -0.5 * c.L : (i == 0 ? 1.0 : -1.0);
+        case DCOL_CYLINDER:
+            if (i < 2) return j == 3 ? -0.5 * c.L : (i == 0 ? 1.0 : -1.0);
+            return j == 3 ? -0.5 * c.L : (i == 2 ? -1.0 : 1.0);
+        default: return 0.0;
+        }
+    }
+    /* soc block: local column j feeds exactly one cone row, soc_row(j), with coefficient soc_c(j) */
+    DCOL_HD static int soc_row(int j)
+    {
+        if (KIND == DCOL_CONE) return j < 3 ? j : 0;
+        return j < 3 ? 1 + j : (j == 3 ? 0 : j - 3); /* ball: y_j -> 1+j, alpha -> 0, e0 -> 1, e1 -> 2 */
+    }
+    DCOL_HD static double soc_c(const Const& c, int j)
+    {
+        if (KIND == DCOL_CONE) return j == 0 ? -c.tanb : (j == 3 ? -0.75 * c.H * c.tanb : -1.0);
+        return j < 3 ? -1.0 : (j == 3 ? -c.R : 1.0);
+    }
+
+    /* pose -> (Q', r')   problem_matrices.py:272-364 */
+    DCOL_HD void set_pose(const Const& c, const double r[3], const double Qm[3][3])
+    {
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            rp[i] = r[i] + (Qm[i][0] * c.r_off[0] + Qm[i][1] * c.r_off[1] + Qm[i][2] * c.r_off[2]);
+            DCOL_UNROLL
+            for (int j = 0; j < 3; ++j)
+                Qp[i][j] = rot ? (Qm[i][0] * c.Q_off[0][j] + Qm[i][1] * c.Q_off[1][j] + Qm[i][2] * c.Q_off[2][j])
+                               : (i == j ? 1.0 : 0.0);
+        }
+    }
+
+    /* world vector v[N] -> local xh[NL];  AFFINE subtracts r' (points), otherwise directions */
+    template <int N, bool AFFINE>
+    DCOL_HD void to_local(const double (&v)[N], int col_e, double (&xh)[NL]) const
+    {
+        double d[3];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) d[i] = AFFINE ? v[i] - rp[i] : v[i];
+        DCOL_UNROLL
+        for (int j = 0; j < 3; ++j) xh[j] = rot ? (Qp[0][j] * d[0] + Qp[1][j] * d[1] + Qp[2][j] * d[2]) : d[j];
+        xh[3] = v[3];
+        DCOL_UNROLL
+        for (int j = 0; j < NE; ++j) xh[4 + j] = v[col_e + j];
+    }
+    /* out[N] += T^T acc  (adjoint of the linear part of to_local) */
+    template <int N>
+    DCOL_HD void from_local_add(const double (&acc)[NL], int col_e, double (&out)[N]) const
+    {
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i)
+            out[i] += rot ? (Qp[i][0] * acc[0] + Qp[i][1] * acc[1] + Qp[i][2] * acc[2]) : acc[i];
+        out[3] += acc[3];
+        DCOL_UNROLL
+        for (int j = 0; j < NE; ++j) out[col_e + j] += acc[4 + j];
+    }
+    /* M[N][N] (upper triangle) += T^T Gl T for a symmetric local matrix Gl (upper triangle valid) */
+    template <int N>
+    DCOL_HD void gram_from_local(const double (&Gl)[NL][NL], int col_e, double (&M)[N][N]) const
+    {
+        if (rot) {
+            double T[3][3]; /* T = Q' Gl_yy */
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) {
+                    double t = 0.0;
+                    DCOL_UNROLL
+                    for (int k = 0; k < 3; ++k) t += Qp[i][k] * (k <= j ? Gl[k][j] : Gl[j][k]);
+                    T[i][j] = t;
+                }
+            }
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                DCOL_UNROLL
+                for (int j = i; j < 3; ++j) M[i][j] += T[i][0] * Qp[j][0] + T[i][1] * Qp[j][1] + T[i][2] * Qp[j][2];
+            }
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                M[i][3] += Qp[i][0] * Gl[0][3] + Qp[i][1] * Gl[1][3] + Qp[i][2] * Gl[2][3];
+                DCOL_UNROLL
+                for (int j = 0; j < NE; ++j)
+                    M[i][col_e + j] += Qp[i][0] * Gl[0][4 + j] + Qp[i][1] * Gl[1][4 + j] + Qp[i][2] * Gl[2][4 + j];
+            }
+        } else {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                DCOL_UNROLL
+                for (int j = i; j < 3; ++j) M[i][j] += Gl[i][j];
+                M[i][3] += Gl[i][3];
+                DCOL_UNROLL
+                for (int j = 0; j < NE; ++j) M[i][col_e + j] += Gl[i][4 + j];
+            }
+        }
+        M[3][3] += Gl[3][3];
+        DCOL_UNROLL
+        for (int j = 0; j < NE; ++j) {
+            M[3][col_e + j] += Gl[3][4 + j];
+            DCOL_UNROLL
+            for (int k = j; k < NE; ++k) M[col_e + j][col_e + k] += Gl[4 + j][4 + k];
+        }
+    }
+
+    /* orthant rows applied to a local vector */
+    DCOL_HD static void ort_apply(const Const& c, const double (&xh)[NL], double (&out)[NOA])
+    {
+        const int no = n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < NO; ++i) {
+            if (dyn && i >= no) break;
+            double t = 0.0;
+            DCOL_UNROLL
+            for (int j = 0; j < NL; ++j)
+                if (nz(i, j)) t += g(c, i, j) * xh[j];
+            out[i] = t;
+        }
+    }
+    /* acc[NL] += sum_i cf[i] * row_i */
+    DCOL_HD static void ort_apply_t(const Const& c, const double (&cf)[NOA], double (&acc)[NL])
+    {
+        const int no = n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < NO; ++i) {
+            if (dyn && i >= no) break;
+            DCOL_UNROLL
+            for (int j = 0; j < NL; ++j)
+                if (nz(i, j)) acc[j] += g(c, i, j) * cf[i];
+        }
+    }
+    /* Gl (upper) += sum_i w[i] row_i row_i^T */
+    DCOL_HD static void ort_gram(const Const& c, const double (&w)[NOA], double (&Gl)[NL][NL])
+    {
+        const int no = n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < NO; ++i) {
+            if (dyn && i >= no) break;
+            DCOL_UNROLL
+            for (int j = 0; j < NL; ++j) {
+                if (!nz(i, j)) continue;
+                const double wg = w[i] * g(c, i, j);
+                DCOL_UNROLL
+                for (int k = j; k < NL; ++k)
+                    if (nz(i, k)) Gl[j][k] += wg * g(c, i, k);
+            }
+        }
+    }
+    /* soc rows applied to a local vector */
+    DCOL_HD static void soc_apply(const Const& c, const double (&xh)[NL], double (&out)[QA])
+    {
+        DCOL_UNROLL
+        for (int r = 0; r < Q; ++r) {
+            double t = 0.0;
+            DCOL_UNROLL
+            for (int j = 0; j < NL; ++j)
+                if (soc_row(j) == r) t += soc_c(c, j) * xh[j];
+            out[r] = t;
+        }
+    }
+    DCOL_HD static void soc_apply_t(const Const& c, const double (&v)[QA], double (&acc)[NL])
+    {
+        if constexpr (Q > 0) {
+            DCOL_UNROLL
+            for (int j = 0; j < NL; ++j) acc[j] += soc_c(c, j) * v[soc_row(j)];
+        }
+    }
+    /* Gl (upper) += G_soc^T W2 G_soc for a symmetric Q x Q matrix W2 (upper triangle valid) */
+    DCOL_HD static void soc_gram(const Const& c, const double (&W2)[QA][QA], double (&Gl)[NL][NL])
+    {
+        if (Q == 0) return;
+        DCOL_UNROLL
+        for (int j = 0; j < NL; ++j) {
+            DCOL_UNROLL
+            for (int k = j; k < NL; ++k) {
+                const int rj = soc_row(j), rk = soc_row(k);
+                const double w = rj <= rk ? W2[rj][rk] : W2[rk][rj];
+                Gl[j][k] += (soc_c(c, j) * soc_c(c, k)) * w;
+            }
+        }
+    }
+};
+
+/* ---------------------------------------------------------------------------------------- */
+/* per-primitive block of the iterate and of the per-iteration temporaries                   */
+
+template <class P>
+struct Block {
+    /* iterate */
+    double so[P::NOA], zo[P::NOA]; /* orthant slack / dual                                   */
+    double sq[P::QA], zq[P::QA];   /* second-order-cone slack / dual (body-frame components) */
+    /* orthant temporaries */
+    double rinv[P::NOA]; /* 1 / lambda_i = 1 / sqrt(s_i z_i)                                */
+    double ta[P::NOA];   /* rho~_i = (W^-1 rz)_i, later ds~_i                               */
+    double tb[P::NOA];   /* k_i, later dz~_i                                                */
+    /* soc temporaries */
+    double lam[P::QA], tq[P::QA], kq[P::QA];
+    double wh[P::QA]; /* J wbar = (wbar_0, -wbar_v): W^-1 = (1/eta) Wbar(wh), W = eta Wbar(J wh) */
+    double eta, ieta, bw;
+    double ls_isn, ls_inu, ls_c0; /* shared line-search terms of lambda, pdip.py:39-47      */
+    double irho, il0;             /* 1 / J(lambda), 1 / lambda_0, pdip.py:108-118           */
+};
+
+template <int Q>
+DCOL_HD double socJ(const double (&u)[Q > 0 ? Q : 1])
+{
+    double t = u[0] * u[0];
+    DCOL_UNROLL
+    for (int i = 1; i < Q; ++i) t -= u[i] * u[i];
+    return t;
+}
+
+/* out = Wbar(w) v = (w.v, v_v + (v_0 + (w_v.v_v) b) w_v), b = 1 / (1 + w_0)   NT_scaling.py:380-392 */
+template <int Q>
+DCOL_HD void wbar_apply(const double (&w)[Q > 0 ? Q : 1], double b, double sign, const double (&v)[Q > 0 ? Q : 1],
+                        double scale, double (&out)[Q > 0 ? Q : 1])
+{
+    /* sign = +1 uses w as given, -1 flips its vector part */
+    double d = 0.0;
+    DCOL_UNROLL
+    for (int i = 1; i < Q; ++i) d += w[i] * v[i];
+    d *= sign;
+    out[0] = scale * (w[0] * v[0] + d);
+    const double f = sign * (v[0] + d * b);
+    DCOL_UNROLL
+    for (int i = 1; i < Q; ++i) out[i] = scale * (v[i] + f * w[i]);
+}
+
+/* pdip.py:237-287 over both primitives' blocks.  Works on (so, sq) or (zo, zq) selected by SEL. */
+template <class P, int SEL>
+DCOL_HD void b2c_scan(const typename P::Const& c, const Block<P>& B, bool& any_nonpos, double& mn)
+{
+    const double* o = SEL == 0 ? B.so : B.zo;
+    const int no = P::n_ort(c);
+    DCOL_UNROLL_ROWS
+    for (int i = 0; i < P::NO; ++i) {
+        if (P::dyn && i >= no) break;
+        if (o[i] <= 0.0) any_nonpos = true;
+        mn = min_(mn, o[i]);
+    }
+}
+template <class P, int SEL>
+DCOL_HD void b2c_soc(const Block<P>& B, double& alpha)
+{
+    if (P::Q == 0) return;
+    const double* q = SEL == 0 ? B.sq : B.zq;
+    double nn = 0.0;
+    DCOL_UNROLL
+    for (int i = 1; i < P::Q; ++i) nn += q[i] * q[i];
+    const double res = q[0] - sqrt(nn);
+    if (res <= 0.0) alpha = max_(alpha, -res);
+}
+template <class P, int SEL>
+DCOL_HD void b2c_shift(const typename P::Const& c, Block<P>& B, double shift)
+{
+    double* o = SEL == 0 ? B.so : B.zo;
+    double* q = SEL == 0 ? B.sq : B.zq;
+    const int no = P::n_ort(c);
+    DCOL_UNROLL_ROWS
+    for (int i = 0; i < P::NO; ++i) {
+        if (P::dyn && i >= no) break;
+        o[i] += shift;
+    }
+    if (P::Q > 0) q[0] += shift;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* results of one pair                                                                       */
+template <int N>
+struct PairResult {
+    double x[N];
+    double grad[12];
+    int32_t iters, status;
+};
+
+/* optional per-iteration trace (debug entry point only) */
+struct Trace {
+    double* mu; /* [DCOL_MAX_ITER + 1] or null */
+};
+
+template <class P1, class P2>
+struct Solver {
+    static constexpr int N = 4 + P1::NE + P2::NE;
+    static constexpr int CE1 = 4, CE2 = 4 + P1::NE;
+    typedef typename P1::Const C1;
+    typedef typename P2::Const C2;
+
+    P1 p1;
+    P2 p2;
+    Block<P1> b1;
+    Block<P2> b2;
+    double x[N];
+
+    /* ---- lower Cholesky of the symmetric M (upper triangle valid); Li holds 1/L_jj.
+     * Unblocked, pivot test `<= 0` with NaN passing, as OpenBLAS potf2 behind numpy/scipy. */
+    DCOL_HD static int chol(const double (&M)[N][N], double (&L)[N][N], double (&Li)[N])
+    {
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) {
+            double d = M[j][j];
+            DCOL_UNROLL
+            for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+            if (d <= 0.0) return j + 1;
+            const double ri = rsqrt_(d);
+            L[j][j] = d * ri;
+            Li[j] = ri;
+            DCOL_UNROLL
+            for (int i = j + 1; i < N; ++i) {
+                double v = M[j][i];
+                DCOL_UNROLL
+                for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+                L[i][j] = v * ri;
+            }
+        }
+        return 0;
+    }
+    DCOL_HD static void chol_solve(const double (&L)[N][N], const double (&Li)[N], double (&v)[N])
+    {
+        DCOL_UNROLL
+        for (int i = 0; i < N; ++i) {
+            double t = v[i];
+            DCOL_UNROLL
+            for (int k = 0; k < i; ++k) t -= L[i][k] * v[k];
+            v[i] = t * Li[i];
+        }
+        DCOL_UNROLL
+        for (int i = N - 1; i >= 0; --i) {
+            double t = v[i];
+            DCOL_UNROLL
+            for (int k = i + 1; k < N; ++k) t -= L[k][i] * v[k];
+            v[i] = t * Li[i];
+        }
+    }
+    DCOL_HD static double probe_sym(const double (&M)[N][N], const double (&v)[N])
+    {
+        double t = 0.0;
+        DCOL_UNROLL
+        for (int i = 0; i < N; ++i) {
+            t += nonfinite_probe(v[i]);
+            DCOL_UNROLL
+            for (int j = i; j < N; ++j) t += nonfinite_probe(M[i][j]);
+        }
+        return t;
+    }
+
+    /* ---- rows of G applied to a world vector: fills (ro, rq) = block of G v (- h if AFFINE) */
+    template <class P, bool AFFINE>
+    DCOL_HD static void rows(const P& p, const typename P::Const& c, int col_e, const double (&v)[N],
+                             double (&ro)[P::NOA], double (&rq)[P::QA])
+    {
+        double xh[P::NL];
+        p.template to_local<N, AFFINE>(v, col_e, xh);
+        P::ort_apply(c, xh, ro);
+        P::soc_apply(c, xh, rq);
+    }
+    /* out[N] += block of G^T (co, cq) */
+    template <class P>
+    DCOL_HD static void rows_t(const P& p, const typename P::Const& c, int col_e, const double (&co)[P::NOA],
+                               const double (&cq)[P::QA], double (&out)[N])
+    {
+        double acc[P::NL];
+        DCOL_UNROLL
+        for (int j = 0; j < P::NL; ++j) acc[j] = 0.0;
+        P::ort_apply_t(c, co, acc);
+        P::soc_apply_t(c, cq, acc);
+        p.template from_local_add<N>(acc, col_e, out);
+    }
+
+    /* ---- pdip.py:291-332, one primitive's share of M = G^T G and of G^T h */
+    template <class P>
+    DCOL_HD static void init_accumulate(const P& p, const typename P::Const& c, int col_e, double (&M)[N][N],
+                                        double (&gth)[N])
+    {
+        double Gl[P::NL][P::NL];
+        DCOL_UNROLL
+        for (int i = 0; i < P::NL; ++i) {
+            DCOL_UNROLL
+            for (int j = 0; j < P::NL; ++j) Gl[i][j] = 0.0;
+        }
+        double ones[P::NOA];
+        DCOL_UNROLL
+        for (int i = 0; i < P::NOA; ++i) ones[i] = 1.0;
+        P::ort_gram(c, ones, Gl);
+        double I2[P::QA][P::QA];
+        DCOL_UNROLL
+        for (int i = 0; i < P::QA; ++i) {
+            DCOL_UNROLL
+            for (int j = 0; j < P::QA; ++j) I2[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+        P::soc_gram(c, I2, Gl);
+        p.template gram_from_local<N>(Gl, col_e, M);
+        /* h = -(G 0 - h): rows at the world origin, negated */
+        double zero[N], ro[P::NOA], rq[P::QA];
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) zero[j] = 0.0;
+        rows<P, true>(p, c, col_e, zero, ro, rq);
+        DCOL_UNROLL
+        for (int i = 0; i < P::NOA; ++i) ro[i] = -ro[i];
+        DCOL_UNROLL
+        for (int i = 0; i < P::QA; ++i) rq[i] = -rq[i];
+        rows_t<P>(p, c, col_e, ro, rq, gth);
+    }
+
+    /* ---- NT scaling of one block + everything of pass A that does not need the Newton step.
+     * Accumulates mu*deg, the Gram matrix G~^T G~, G^T z, G~^T (lambda - rho~) and G~^T (lambda^-1 o e). */
+    template <class P>
+    DCOL_HD static double nt_and_mu(const typename P::Const& c, Block<P>& B, double& bad)
+    {
+        double sz = 0.0;
+        const int no = P::n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < P::NO; ++i) {
+            if (P::dyn && i >= no) break;
+            const double pr = B.so[i] * B.zo[i];
+            sz += pr;
+            B.rinv[i] = rsqrt_(pr); /* NT_scaling.py:430: W_ort = sqrt(s/z); lambda = W z = sqrt(s z) */
+        }
+        if (P::Q > 0) {
+            /* NT_scaling.py:340-405 */
+            double dq = 0.0;
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) dq += B.sq[i] * B.zq[i];
+            sz += dq;
+            const double Js = socJ<P::Q>(B.sq), Jz = socJ<P::Q>(B.zq);
+            const double rs = rsqrt_(Js), rz = rsqrt_(Jz);
+            /* gamma = sqrt((1 + zbar.sbar) / 2);  wbar = (sbar + J zbar) / (2 gamma) */
+            const double g2 = 0.5 * (1.0 + dq * (rs * rz));
+            const double ig = 0.5 * rsqrt_(g2);
+            B.wh[0] = (B.sq[0] * rs + B.zq[0] * rz) * ig;
+            DCOL_UNROLL
+            for (int i = 1; i < P::Q; ++i) B.wh[i] = -((B.sq[i] * rs - B.zq[i] * rz) * ig);
+            B.bw = 1.0 / (B.wh[0] + 1.0);
+            /* eta = (J(s)/J(z))^(1/4) */
+            const double e2 = (Js * rs) * rz; /* sqrt(Js / Jz) */
+            B.ieta = rsqrt_(e2);
+            B.eta = e2 * B.ieta;
+            bad += nonfinite_probe(B.eta) + nonfinite_probe(B.ieta) + nonfinite_probe(B.bw);
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) bad += nonfinite_probe(B.wh[i]);
+        }
+        return sz;
+    }
+
+    template <class P>
+    DCOL_HD static void pass_a(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&xx)[N],
+                               double (&M)[N][N], double (&rx)[N], double (&va)[N], double (&vl)[N])
+    {
+        double ro[P::NOA], rq[P::QA];
+        rows<P, true>(p, c, col_e, xx, ro, rq); /* G x - h */
+        double Gl[P::NL][P::NL];
+        DCOL_UNROLL
+        for (int i = 0; i < P::NL; ++i) {
+            DCOL_UNROLL
+            for (int j = 0; j < P::NL; ++j) Gl[i][j] = 0.0;
+        }
+        double w2[P::NOA], ca[P::NOA], cl[P::NOA];
+        double qa[P::QA], ql[P::QA];
+        const int no = P::n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < P::NO; ++i) {
+            if (P::dyn && i >= no) break;
+            const double ri = B.rinv[i];
+            const double winv = B.zo[i] * ri;            /* 1 / w_i                       */
+            const double lam = (B.so[i] * B.zo[i]) * ri; /* lambda_i                      */
+            const double rho = winv * (B.so[i] + ro[i]); /* (W^-1 rz)_i, rz = s + G x - h */
+            B.ta[i] = rho;
+            w2[i] = winv * winv;
+            ca[i] = winv * (lam - rho); /* W^-1 b~_affine */
+            cl[i] = winv * ri;          /* W^-1 (lambda^-1 o e) */
+        }
+        P::ort_gram(c, w2, Gl);
+        if (P::Q > 0) {
+            /* lambda = W z */
+            wbar_apply<P::Q>(B.wh, B.bw, -1.0, B.zq, B.eta, B.lam);
+            double rzq[P::QA];
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) rzq[i] = B.sq[i] + rq[i];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, rzq, B.ieta, B.tq); /* rho~ = W^-1 rz */
+            /* explicit W^-1 and W^-2 = W^-T W^-1 for the Gram block */
+            double Wi[P::QA][P::QA], W2[P::QA][P::QA];
+            Wi[0][0] = B.ieta * B.wh[0];
+            DCOL_UNROLL
+            for (int i = 1; i < P::Q; ++i) {
+                Wi[0][i] = Wi[i][0] = B.ieta * B.wh[i];
+                DCOL_UNROLL
+                for (int j = i; j < P::Q; ++j)
+                    Wi[i][j] = Wi[j][i] = B.ieta * ((i == j ? 1.0 : 0.0) + B.bw * (B.wh[i] * B.wh[j]));
+            }
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) {
+                DCOL_UNROLL
+                for (int j = i; j < P::Q; ++j) {
+                    double t = 0.0;
+                    DCOL_UNROLL
+                    for (int r = 0; r < P::Q; ++r) t += Wi[r][i] * Wi[r][j];
+                    W2[i][j] = t;
+                }
+            }
+            P::soc_gram(c, W2, Gl);
+            /* shared scalars of lambda: inverse cone product (pdip.py:108-118) and line search (pdip.py:39-47) */
+            const double Jl = socJ<P::Q>(B.lam);
+            B.irho = 1.0 / Jl;
+            B.il0 = 1.0 / B.lam[0];
+            const double nu = max_(Jl, 1e-25);
+            B.ls_isn = rsqrt_(nu);
+            B.ls_inu = B.ls_isn * B.ls_isn;
+            B.ls_c0 = 1.0 / (B.lam[0] * B.ls_isn + 1.0);
+            /* W^-1 (lambda - rho~) and W^-1 (lambda^-1 o e), lambda^-1 o e = (lambda_0, -lambda_v) / J(lambda) */
+            double t1[P::QA], t2[P::QA];
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) {
+                t1[i] = B.lam[i] - B.tq[i];
+                t2[i] = (i == 0 ? B.lam[i] : -B.lam[i]) * B.irho;
+            }
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, t1, B.ieta, qa);
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, t2, B.ieta, ql);
+        }
+        p.template gram_from_local<N>(Gl, col_e, M);
+        rows_t<P>(p, c, col_e, B.zo, B.zq, rx);
+        rows_t<P>(p, c, col_e, ca, qa, va);
+        rows_t<P>(p, c, col_e, cl, ql, vl);
+    }
+
+    /* ---- line-search measure of a scaled direction against lambda: the step is 1/t for t > 1.
+     * orthant pdip.py:7-22, soc pdip.py:25-52 */
+    template <class P>
+    DCOL_HD static double soc_ls(const Block<P>& B, const double (&d)[P::QA])
+    {
+        double zeta = B.lam[0] * d[0];
+        DCOL_UNROLL
+        for (int i = 1; i < P::Q; ++i) zeta -= B.lam[i] * d[i];
+        const double rho0 = zeta * B.ls_inu;
+        const double coef = (zeta * B.ls_isn + d[0]) * B.ls_c0;
+        double nn = 0.0;
+        DCOL_UNROLL
+        for (int i = 1; i < P::Q; ++i) {
+            const double rv = d[i] * B.ls_isn - coef * (B.lam[i] * B.ls_inu);
+            nn += rv * rv;
+        }
+        return sqrt(nn) - rho0;
+    }
+
+    /* ---- pass B: affine direction of one block, its line-search measures, the three dot products of
+     * the centring ratio, k = lambda^-1 o (ds~ o dz~) and G~^T k */
+    template <class P>
+    DCOL_HD static void pass_b(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
+                               double& ts, double& tz, double& d_ls, double& d_lz, double& d_sz, double (&vk)[N])
+    {
+        double ro[P::NOA], rq[P::QA];
+        rows<P, false>(p, c, col_e, dx, ro, rq); /* G dx */
+        double ck[P::NOA], qk[P::QA];
+        const int no = P::n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < P::NO; ++i) {
+            if (P::dyn && i >= no) break;
+            const double ri = B.rinv[i];
+            const double winv = B.zo[i] * ri;
+            const double lam = (B.so[i] * B.zo[i]) * ri;
+            const double dz = winv * ro[i] - (lam - B.ta[i]); /* dz~ = G~ dx - b~ */
+            const double ds = -lam - dz;                      /* ds~ = d - dz~, d = -lambda */
+            ts = max_(ts, -ds * ri);
+            tz = max_(tz, -dz * ri);
+            d_ls += lam * ds;
+            d_lz += lam * dz;
+            d_sz += ds * dz;
+            const double k = (ds * dz) * ri;
+            B.tb[i] = k;
+            ck[i] = winv * k;
+        }
+        if (P::Q > 0) {
+            double g[P::QA], dz[P::QA], ds[P::QA], w[P::QA];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, rq, B.ieta, g); /* G~ dx */
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) {
+                dz[i] = g[i] - (B.lam[i] - B.tq[i]);
+                ds[i] = -B.lam[i] - dz[i];
+                d_ls += B.lam[i] * ds[i];
+                d_lz += B.lam[i] * dz[i];
+                d_sz += ds[i] * dz[i];
+            }
+            ts = max_(ts, soc_ls<P>(B, ds));
+            tz = max_(tz, soc_ls<P>(B, dz));
+            /* w = ds~ o dz~ (pdip.py:165-200); k = lambda^-1 o w (pdip.py:88-122) */
+            w[0] = 0.0;
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) w[0] += ds[i] * dz[i];
+            DCOL_UNROLL
+            for (int i = 1; i < P::Q; ++i) w[i] = ds[0] * dz[i] + dz[0] * ds[i];
+            double nu = 0.0;
+            DCOL_UNROLL
+            for (int i = 1; i < P::Q; ++i) nu += B.lam[i] * w[i];
+            B.kq[0] = B.irho * (B.lam[0] * w[0] - nu);
+            const double c1 = nu * B.il0 - w[0], c2 = B.il0; /* (rho / lambda_0) / rho */
+            DCOL_UNROLL
+            for (int i = 1; i < P::Q; ++i) B.kq[i] = B.irho * (c1 * B.lam[i]) + c2 * w[i];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.kq, B.ieta, qk);
+        }
+        rows_t<P>(p, c, col_e, ck, qk, vk);
+    }
+
+    /* ---- pass C: corrector direction of one block (stored as ds~ in ta/tq, dz~ in tb/kq) and its
+     * line-search measures */
+    template <class P>
+    DCOL_HD static void pass_c(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
+                               double sigmu, double& ts, double& tz)
+    {
+        double ro[P::NOA], rq[P::QA];
+        rows<P, false>(p, c, col_e, dx, ro, rq);
+        const int no = P::n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < P::NO; ++i) {
+            if (P::dyn && i >= no) break;
+            const double ri = B.rinv[i];
+            const double winv = B.zo[i] * ri;
+            const double lam = (B.so[i] * B.zo[i]) * ri;
+            const double d = -lam - B.tb[i] + sigmu * ri; /* lambda^-1 o ds */
+            const double bt = -B.ta[i] - d;               /* b~ = -rho~ - d  */
+            const double dz = winv * ro[i] - bt;
+            const double ds = d - dz;
+            ts = max_(ts, -ds * ri);
+            tz = max_(tz, -dz * ri);
+            B.ta[i] = ds;
+            B.tb[i] = dz;
+        }
+        if (P::Q > 0) {
+            double g[P::QA], dz[P::QA], ds[P::QA];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, rq, B.ieta, g);
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) {
+                const double li = (i == 0 ? B.lam[i] : -B.lam[i]) * B.irho; /* lambda^-1 o e */
+                const double d = -B.lam[i] - B.kq[i] + sigmu * li;
+                const double bt = -B.tq[i] - d;
+                dz[i] = g[i] - bt;
+                ds[i] = d - dz[i];
+            }
+            ts = max_(ts, soc_ls<P>(B, ds));
+            tz = max_(tz, soc_ls<P>(B, dz));
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) {
+                B.tq[i] = ds[i];
+                B.kq[i] = dz[i];
+            }
+        }
+    }
+
+    /* ---- s += a W ds~,  z += a W^-1 dz~   pdip.py:464-466 */
+    template <class P>
+    DCOL_HD static void pass_d(const typename P::Const& c, Block<P>& B, double a)
+    {
+        const int no = P::n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < P::NO; ++i) {
+            if (P::dyn && i >= no) break;
+            const double ri = B.rinv[i];
+            const double w = B.so[i] * ri, winv = B.zo[i] * ri;
+            B.so[i] += a * (w * B.ta[i]);
+            B.zo[i] += a * (winv * B.tb[i]);
+        }
+        if (P::Q > 0) {
+            double ds[P::QA], dz[P::QA];
+            wbar_apply<P::Q>(B.wh, B.bw, -1.0, B.tq, B.eta, ds);
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.kq, B.ieta, dz);
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) {
+                B.sq[i] += a * ds[i];
+                B.zq[i] += a * dz[i];
+            }
+        }
+    }
+
+    /* ---- gradient share of one primitive: d/d(r, p) of z^T (G(theta) x - h(theta)), (x, z) frozen.
+     * proximity_gradient.py:8-88 by the chain rule instead of finite differences. */
+    template <class P>
+    DCOL_HD void grad_block(const P& p, const typename P::Const& c, int col_e, const Block<P>& B, const double pm[3],
+                            const double Qm[3][3], double* g6) const
+    {
+        /* u = y-part of the local adjoint product of the rows whose coefficients are constant in the body
+         * frame (all orthant rows, the cone's soc rows); the ball soc rows -(x - r') + Q' E e are written in
+         * world axes by the reference, so their dual is frozen in world components: zw = Q' z_v. */
+        double acc[P::NL];
+        DCOL_UNROLL
+        for (int j = 0; j < P::NL; ++j) acc[j] = 0.0;
+        P::ort_apply_t(c, B.zo, acc);
+        if (P::Q > 0 && !P::ball) P::soc_apply_t(c, B.zq, acc);
+        double d[3], gr[3], Mq[3][3];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) d[i] = x[i] - p.rp[i];
+        /* gr = dL/dr' = -Q' u (+ zw);  Mq = dL/dQ(p) = d (Q_off u)^T + zw (Q_off ehat)^T + gr r_off^T */
+        double zw[3] = { 0.0, 0.0, 0.0 }, eh[3] = { 0.0, 0.0, 0.0 };
+        if (P::ball) {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i)
+                zw[i] = P::rot ? (p.Qp[i][0] * B.zq[1] + p.Qp[i][1] * B.zq[2] + p.Qp[i][2] * B.zq[3]) : B.zq[1 + i];
+            DCOL_UNROLL
+            for (int j = 0; j < P::NE; ++j) eh[j] = x[col_e + j];
+        }
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i)
+            gr[i] = zw[i] - (P::rot ? (p.Qp[i][0] * acc[0] + p.Qp[i][1] * acc[1] + p.Qp[i][2] * acc[2]) : acc[i]);
+        double qu[3], qe[3];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            qu[i] = c.Q_off[i][0] * acc[0] + c.Q_off[i][1] * acc[1] + c.Q_off[i][2] * acc[2];
+            qe[i] = c.Q_off[i][0] * eh[0] + c.Q_off[i][1] * eh[1] + c.Q_off[i][2] * eh[2];
+        }
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            DCOL_UNROLL
+            for (int j = 0; j < 3; ++j) Mq[i][j] = (P::rot ? d[i] * qu[j] + zw[i] * qe[j] : 0.0) + gr[i] * c.r_off[j];
+        }
+        g6[0] = gr[0];
+        g6[1] = gr[1];
+        g6[2] = gr[2];
+        dcm_derivative_contract(pm, Qm, Mq, g6 + 3);
+    }
+
+    /* ---- the whole solve.  pose = (r, p).  Returns the status word; fills res. */
+    DCOL_HD int solve(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double tol, int max_iter,
+                      bool want_grad, PairResult<N>& res, const Trace* trace)
+    {
+        double Q1[3][3], Q2[3][3];
+        dcm_from_mrp(pose1 + 3, Q1);
+        dcm_from_mrp(pose2 + 3, Q2);
+        p1.set_pose(c1, pose1, Q1);
+        p2.set_pose(c2, pose2, Q2);
+        res.iters = 0;
+
+        double L[N][N], Li[N];
+        /* -------- initial point, pdip.py:291-332 -------- */
+        {
+            double M[N][N], gth[N];
+            DCOL_UNROLL
+            for (int i = 0; i < N; ++i) {
+                gth[i] = 0.0;
+                DCOL_UNROLL
+                for (int j = 0; j < N; ++j) M[i][j] = 0.0;
+            }
+            init_accumulate<P1>(p1, c1, CE1, M, gth);
+            init_accumulate<P2>(p2, c2, CE2, M, gth);
+            if (chol(M, L, Li)) return res.status = DCOL_STATUS_NOT_PD;
+            if (probe_sym(M, gth) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) x[j] = gth[j];
+            chol_solve(L, Li, x); /* x_hat = (G^T G)^-1 G^T h */
+            rows<P1, true>(p1, c1, CE1, x, b1.so, b1.sq);
+            rows<P2, true>(p2, c2, CE2, x, b2.so, b2.sq); /* s~ = G x_hat - h */
+            /* solve_triangular(F, -c) reads the UPPER triangle of the lower factor, i.e. its diagonal
+             * (pdip.py:326); then a proper back substitution with F^T */
+            double xd[N];
+            DCOL_UNROLL
+            for (int i = 0; i < N; ++i) xd[i] = (i == 3) ? -Li[3] : 0.0;
+            DCOL_UNROLL
+            for (int i = N - 1; i >= 0; --i) {
+                double t = xd[i];
+                DCOL_UNROLL
+                for (int k = i + 1; k < N; ++k) t -= L[k][i] * xd[k];
+                xd[i] = t * Li[i];
+            }
+            rows<P1, false>(p1, c1, CE1, xd, b1.zo, b1.zq);
+            rows<P2, false>(p2, c2, CE2, xd, b2.zo, b2.zq); /* z~ = G x */
+            bring2cone<0>(c1, c2);
+            bring2cone<1>(c1, c2);
+        }
+
+        const int deg = P1::n_ort(c1) + P2::n_ort(c2) + (P1::Q > 0) + (P2::Q > 0);
+        const double ideg = 1.0 / (double)deg;
+
+        for (int it = 0; it < max_iter; ++it) {
+            res.iters = it;
+            double bad = 0.0;
+            double sz = nt_and_mu<P1>(c1, b1, bad);
+            sz += nt_and_mu<P2>(c2, b2, bad);
+            if (bad != 0.0) return res.status = DCOL_STATUS_NON_FINITE; /* cho_factor(W_soc) check_finite */
+            const double mu = sz * ideg;
+            if (trace && trace->mu) trace->mu[it] = mu;
+            if (mu < tol) return res.status = DCOL_STATUS_OK; /* the only convergence test, pdip.py:418-422 */
+
+            double M[N][N], rx[N], va[N], vl[N];
+            DCOL_UNROLL
+            for (int i = 0; i < N; ++i) {
+                rx[i] = (i == 3) ? 1.0 : 0.0; /* + c */
+                va[i] = vl[i] = 0.0;
+                DCOL_UNROLL
+                for (int j = 0; j < N; ++j) M[i][j] = 0.0;
+            }
+            pass_a<P1>(p1, c1, CE1, b1, x, M, rx, va, vl);
+            pass_a<P2>(p2, c2, CE2, b2, x, M, rx, va, vl);
+            double dx[N];
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) dx[j] = va[j] - rx[j]; /* bx + G~^T b~ */
+            if (probe_sym(M, dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
+            if (chol(M, L, Li)) return res.status = DCOL_STATUS_NOT_PD;
+            chol_solve(L, Li, dx);
+
+            /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
+            double ts = 0.0, tz = 0.0, d_ls = 0.0, d_lz = 0.0, d_sz = 0.0, vk[N];
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) vk[j] = 0.0;
+            pass_b<P1>(p1, c1, CE1, b1, dx, ts, tz, d_ls, d_lz, d_sz, vk);
+            pass_b<P2>(p2, c2, CE2, b2, dx, ts, tz, d_ls, d_lz, d_sz, vk);
+            double t = max_(ts, tz);
+            double a = t > 1.0 ? 1.0 / t : 1.0;
+            const double rho = (sz + a * (d_ls + d_lz) + (a * a) * d_sz) / sz;
+            const double cl = max_(0.0, min_(1.0, rho));
+            const double sigmu = (cl * cl * cl) * mu;
+
+            /* corrector: rhs = rhs_affine + G~^T k - sigma mu G~^T (lambda^-1 o e), same factor   pdip.py:450-460 */
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) dx[j] = (va[j] - rx[j]) + vk[j] - sigmu * vl[j];
+            if (probe_sym(M, dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
+            chol_solve(L, Li, dx);
+            ts = 0.0;
+            tz = 0.0;
+            pass_c<P1>(p1, c1, CE1, b1, dx, sigmu, ts, tz);
+            pass_c<P2>(p2, c2, CE2, b2, dx, sigmu, ts, tz);
+            t = max_(ts, tz);
+            a = min_(1.0, 0.99 * (t > 1.0 ? 1.0 / t : 1.0)); /* pdip.py:462 */
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) x[j] += a * dx[j];
+            pass_d<P1>(c1, b1, a);
+            pass_d<P2>(c2, b2, a);
+        }
+        res.iters = max_iter;
+        return res.status = DCOL_STATUS_MAX_ITER; /* pdip.py:470 */
+    }
+
+    template <int SEL>
+    DCOL_HD void bring2cone(const C1& c1, const C2& c2)
+    {
+        double alpha = -1.0, mn = INFINITY;
+        bool any = false;
+        b2c_scan<P1, SEL>(c1, b1, any, mn);
+        b2c_scan<P2, SEL>(c2, b2, any, mn);
+        if (any) alpha = -mn;
+        b2c_soc<P1, SEL>(b1, alpha);
+        b2c_soc<P2, SEL>(b2, alpha);
+        if (alpha < 0.0) return;
+        b2c_shift<P1, SEL>(c1, b1, 1.0 + alpha);
+        b2c_shift<P2, SEL>(c2, b2, 1.0 + alpha);
+    }
+
+    DCOL_HD void gradient(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double* grad) const
+    {
+        double Q1[3][3], Q2[3][3];
+        dcm_from_mrp(pose1 + 3, Q1);
+        dcm_from_mrp(pose2 + 3, Q2);
+        grad_block<P1>(p1, c1, CE1, b1, pose1 + 3, Q1, grad);
+        grad_block<P2>(p2, c2, CE2, b2, pose2 + 3, Q2, grad + 6);
+    }
+
+    /* world-frame (s, z) in the reference's row order [ort1; ort2; soc1; soc2] (debug entry point) */
+    template <class P>
+    DCOL_HD static void export_soc(const P& p, const double (&q)[P::QA], double* out)
+    {
+        if (P::Q == 0) return;
+        if (P::ball && P::rot) {
+            out[0] = q[0];
+            for (int i = 0; i < 3; ++i) out[1 + i] = p.Qp[i][0] * q[1] + p.Qp[i][1] * q[2] + p.Qp[i][2] * q[3];
+        } else {
+            for (int i = 0; i < P::Q; ++i) out[i] = q[i];
+        }
+    }
+    DCOL_HD int export_sz(const C1& c1, const C2& c2, double* s, double* z) const
+    {
+        int r = 0;
+        for (int i = 0; i < P1::n_ort(c1); ++i, ++r) { s[r] = b1.so[i]; z[r] = b1.zo[i]; }
+        for (int i = 0; i < P2::n_ort(c2); ++i, ++r) { s[r] = b2.so[i]; z[r] = b2.zo[i]; }
+        export_soc<P1>(p1, b1.sq, s + r); export_soc<P1>(p1, b1.zq, z + r); r += P1::Q;
+        export_soc<P2>(p2, b2.sq, s + r); export_soc<P2>(p2, b2.zq, z + r); r += P2::Q;
+        return r;
+    }
+};
+
+} /* namespace dcol */
+#endif /* DCOL_SOLVER_CUH_ */

@@ -1,0 +1,245 @@
+"""Batched proximity solve + gradient: the Python host above the C ABI.
+
+New entry points (the reference evaluates pairs one by one in Python loops,
+``systems/cluttered_hallway_quadrotor.py:131-133,155``):
+
+* :class:`ProximityEngine` — owns a shape table on one GPU; ``plan()`` groups a batch of
+  (shape, shape) index pairs once, ``solve()`` runs every pair of the plan on device buffers,
+  ``solve_host()`` takes NumPy buffers through the chunked copy/solve pipeline of the C ABI.
+* :func:`proximity_batch` — convenience over lists of primitive objects.
+
+PyTorch is only the buffer carrier (device memory, streams); all arithmetic happens in
+``libdcol_b200.so``.  Status words follow ``include/dcol.h``; :func:`raise_for_status` maps them to
+the exception classes the reference raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .shapes import (STATUS_MAX_ITER, STATUS_NON_FINITE, STATUS_NOT_PD, STATUS_OK, STATUS_UNSUPPORTED, flatten_shapes,
+                     pose_of)
+
+WANT_CONTACT, WANT_GRAD = _lib.WANT_CONTACT, _lib.WANT_GRAD
+
+
+def raise_for_status(status: int):
+    """Re-raise what the reference raises for a failed solve (pdip.py:470, SciPy check_finite,
+    numpy/scipy Cholesky, combine_problem_matrices.py:58-67)."""
+    if status == STATUS_OK:
+        return
+    if status == STATUS_MAX_ITER:
+        raise Exception("Maximum number of iterations reached, PDIP failed")
+    if status == STATUS_NON_FINITE:
+        raise ValueError("array must not contain infs or NaNs")
+    if status == STATUS_NOT_PD:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    if status == STATUS_UNSUPPORTED:
+        raise ValueError("all the input array dimensions except for the concatenation axis must match exactly "
+                         "(both primitives carry extra decision variables)")
+    raise RuntimeError(f"unknown DCOL status {status}")
+
+
+@dataclass
+class BatchResult:
+    """Outputs of one batched solve (torch CUDA tensors from ``solve``, NumPy arrays from ``solve_host``)."""
+    alpha: object      # [B]      proximity value, NaN where status != 0
+    contact: object    # [B, 3]   x[0:3] of the solution, or None
+    grad: object       # [B, 12]  d alpha / d [r1 p1 r2 p2], or None
+    iters: object      # [B]      PDIP iterations taken
+    status: object     # [B]      DCOL_STATUS_*
+
+
+class Plan:
+    """A batch's pairs grouped by shape pair (device counting sort), reusable across solves."""
+
+    def __init__(self, engine, idx1, idx2):
+        import torch
+        self.engine = engine
+        self.idx1 = idx1.to(device=engine.device, dtype=torch.int32).contiguous()
+        self.idx2 = idx2.to(device=engine.device, dtype=torch.int32).contiguous()
+        if self.idx1.shape != self.idx2.shape or self.idx1.dim() != 1:
+            raise ValueError("idx1 and idx2 must be 1-D and of equal length")
+        self.size = int(self.idx1.shape[0])
+        handle = C.c_void_p()
+        stream = torch.cuda.current_stream(engine.device).cuda_stream
+        _lib.check(_lib.lib().dcol_plan_create(engine._table, self.idx1.data_ptr(), self.idx2.data_ptr(), self.size,
+                                               stream, C.byref(handle)))
+        self._handle = handle
+        self.n_groups = int(_lib.lib().dcol_plan_n_groups(handle))
+        self.n_launches = int(_lib.lib().dcol_plan_n_launches(handle))
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            _lib.lib().dcol_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ProximityEngine:
+    """Shape table on one CUDA device + batched solves against it."""
+
+    def __init__(self, shapes, device: int = 0):
+        L = _lib.lib()
+        if L.dcol_device_count() <= 0:
+            raise RuntimeError("no CUDA device visible: the DCOL B200 engine has no CPU fallback")
+        import torch
+        self.device = torch.device("cuda", device)
+        if isinstance(shapes, tuple) and len(shapes) == 3:
+            self.records, self.A, self.b = shapes
+        else:
+            self.records, self.A, self.b = flatten_shapes(list(shapes))
+        self.records = np.ascontiguousarray(self.records)
+        self.A = np.ascontiguousarray(self.A, dtype=np.float64).reshape(-1, 3)
+        self.b = np.ascontiguousarray(self.b, dtype=np.float64).reshape(-1)
+        handle = C.c_void_p()
+        nf = int(self.b.shape[0])
+        _lib.check(L.dcol_shape_table_create(self.records.ctypes.data, len(self.records),
+                                             self.A.ctypes.data if nf else None, self.b.ctypes.data if nf else None,
+                                             nf, device, C.byref(handle)))
+        self._table = handle
+
+    def close(self):
+        if getattr(self, "_table", None):
+            _lib.lib().dcol_shape_table_destroy(self._table)
+            self._table = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device buffers
+    def plan(self, idx1, idx2) -> Plan:
+        import torch
+        return Plan(self, torch.as_tensor(idx1), torch.as_tensor(idx2))
+
+    def solve(self, plan: Plan, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
+              want_contact: bool = True, out: BatchResult | None = None) -> BatchResult:
+        """Enqueue the solve of every pair of ``plan`` on the current CUDA stream.
+
+        ``pose1``/``pose2``: float64 CUDA tensors ``[B, 6]`` (rows ``r, p``).  Returns CUDA tensors;
+        the call does not synchronise."""
+        import torch
+        B = plan.size
+        for name, t in (("pose1", pose1), ("pose2", pose2)):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (B, 6)):
+                raise ValueError(f"{name} must be a contiguous float64 CUDA tensor of shape ({B}, 6)")
+        if out is None:
+            dev = self.device
+            out = BatchResult(
+                alpha=torch.empty(B, dtype=torch.float64, device=dev),
+                contact=torch.empty((B, 3), dtype=torch.float64, device=dev) if want_contact else None,
+                grad=torch.empty((B, 12), dtype=torch.float64, device=dev) if want_grad else None,
+                iters=torch.empty(B, dtype=torch.int32, device=dev),
+                status=torch.empty(B, dtype=torch.int32, device=dev))
+        flags = (WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().dcol_proximity_batch_device(
+            plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter), flags, out.alpha.data_ptr(),
+            out.contact.data_ptr() if out.contact is not None else None,
+            out.grad.data_ptr() if out.grad is not None else None, out.iters.data_ptr(), out.status.data_ptr(), stream))
+        return out
+
+    # ------------------------------------------------------------------ host buffers
+    def solve_host(self, idx1, idx2, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
+                   want_contact: bool = True, out: BatchResult | None = None) -> BatchResult:
+        """The reference-facing call: NumPy buffers in, NumPy buffers out, copies inside."""
+        idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
+        idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
+        pose1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(-1, 6)
+        pose2 = np.ascontiguousarray(pose2, dtype=np.float64).reshape(-1, 6)
+        B = int(idx1.shape[0])
+        if not (idx2.shape[0] == B and pose1.shape[0] == B and pose2.shape[0] == B):
+            raise ValueError("idx1, idx2, pose1, pose2 must describe the same number of pairs")
+        if out is None:
+            out = BatchResult(alpha=np.empty(B), contact=np.empty((B, 3)) if want_contact else None,
+                              grad=np.empty((B, 12)) if want_grad else None, iters=np.empty(B, np.int32),
+                              status=np.empty(B, np.int32))
+        flags = (WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
+        _lib.check(_lib.lib().dcol_proximity_batch_host(
+            self._table, idx1.ctypes.data, idx2.ctypes.data, pose1.ctypes.data, pose2.ctypes.data, B, float(tol),
+            int(max_iter), flags, out.alpha.ctypes.data, out.contact.ctypes.data if out.contact is not None else None,
+            out.grad.ctypes.data if out.grad is not None else None, out.iters.ctypes.data, out.status.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ debugging
+    def trace_pair(self, i1: int, i2: int, pose1, pose2, tol: float = 1e-6) -> dict:
+        """One pair with the per-iteration ``mu`` trace and the final world-frame ``(x, s, z)``."""
+        pose1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(6)
+        pose2 = np.ascontiguousarray(pose2, dtype=np.float64).reshape(6)
+        alpha = C.c_double()
+        x, s, z = np.full(_lib.MAX_N, np.nan), np.full(_lib.MAX_M, np.nan), np.full(_lib.MAX_M, np.nan)
+        mu = np.full(_lib.MAX_ITER + 1, np.nan)
+        n, m, iters, status = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().dcol_debug_trace_pair(
+            self._table, int(i1), int(i2), pose1.ctypes.data, pose2.ctypes.data, float(tol),
+            C.cast(C.byref(alpha), C.c_void_p), x.ctypes.data, s.ctypes.data, z.ctypes.data,
+            C.cast(C.byref(n), C.c_void_p), C.cast(C.byref(m), C.c_void_p), C.cast(C.byref(iters), C.c_void_p),
+            C.cast(C.byref(status), C.c_void_p), mu.ctypes.data))
+        return dict(alpha=alpha.value, x=x[:n.value], s=s[:m.value], z=z[:m.value], iters=iters.value,
+                    status=status.value, mu=mu, n=n.value, m=m.value)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A page-locked NumPy array (``dcol_host_alloc``): host buffers handed to ``solve_host`` copy
+    asynchronously at PCIe rate when they live in such memory."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    _lib.check(_lib.lib().dcol_host_alloc(n, C.byref(ptr)))
+    buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = ptr
+    return arr
+
+
+def pinned_free(arr):
+    ptr = _PINNED.pop(arr.ctypes.data, None)
+    if ptr is not None:
+        _lib.lib().dcol_host_free(ptr)
+
+
+_PINNED: dict = {}
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of the device in FLOP/s (the roofline denominator)."""
+    v = C.c_double()
+    _lib.check(_lib.lib().dcol_measure_fp64_peak(int(device), C.byref(v)))
+    return v.value
+
+
+def proximity_batch(prims1, prims2, pdip_tol: float = 1e-6, want_grad: bool = True, device: int = 0) -> BatchResult:
+    """Evaluate ``proximity_gradient(prims1[k], prims2[k])`` for all k in one call.
+
+    ``prims1``/``prims2`` are equally long sequences of primitive objects (poses are read from
+    ``.r`` / ``.p`` now).  Objects that are the same Python object share one shape record.
+    Returns NumPy arrays; failures are reported in ``status`` (use :func:`raise_for_status`)."""
+    if len(prims1) != len(prims2):
+        raise ValueError("prims1 and prims2 must have the same length")
+    uniq, index = [], {}
+    idx = np.empty((2, len(prims1)), dtype=np.int32)
+    poses = np.empty((2, len(prims1), 6))
+    for side, prims in enumerate((prims1, prims2)):
+        for k, prim in enumerate(prims):
+            j = index.get(id(prim))
+            if j is None:
+                j = index[id(prim)] = len(uniq)
+                uniq.append(prim)
+            idx[side, k] = j
+            poses[side, k] = pose_of(prim)
+    eng = ProximityEngine(uniq, device=device)
+    try:
+        return eng.solve_host(idx[0], idx[1], poses[0], poses[1], tol=pdip_tol, want_grad=want_grad)
+    finally:
+        eng.close()

@@ -1,0 +1,88 @@
+"""Multi-GPU plumbing: one process per GPU, the batch sharded by contiguous ranges, results
+returned with ONE all-gather (BASELINE.json north_star).
+
+Every (candidate x knot x obstacle) pair is an independent solve, so there is no exchange during
+the solve.  The solve writes its outputs straight into one flat buffer per rank,
+
+    [ alpha (B) | grad (12 B) | contact (3 B) | iters, status (B int32 pairs) ]   float64 words
+
+so the gather is a single ``all_gather_into_tensor`` over NVLink with no packing pass.
+Works with any ``torch.distributed`` backend (NCCL on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import BatchResult
+
+WORDS_PER_PAIR = 1 + 12 + 3 + 1   # float64 words of one pair's record (136 bytes)
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced split of ``n_items`` (first ``n_items % world`` ranks get one more)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def packed_views(flat: torch.Tensor, B: int) -> BatchResult:
+    """Views of one rank's flat record buffer (``WORDS_PER_PAIR * B`` float64 words)."""
+    if flat.dtype != torch.float64 or flat.numel() != WORDS_PER_PAIR * B or not flat.is_contiguous():
+        raise ValueError("flat must be a contiguous float64 tensor of WORDS_PER_PAIR * B words")
+    alpha = flat[:B]
+    grad = flat[B:13 * B].view(B, 12)
+    contact = flat[13 * B:16 * B].view(B, 3)
+    ints = flat[16 * B:17 * B].view(torch.int32)          # 2 B int32 words
+    return BatchResult(alpha=alpha, contact=contact, grad=grad, iters=ints[:B], status=ints[B:])
+
+
+def alloc_packed(B: int, device) -> tuple[torch.Tensor, BatchResult]:
+    flat = torch.empty(WORDS_PER_PAIR * B, dtype=torch.float64, device=device)
+    return flat, packed_views(flat, B)
+
+
+def all_gather_packed(flat: torch.Tensor, B: int, world: int, out: torch.Tensor | None = None, group=None,
+                      async_op: bool = False):
+    """Gather every rank's flat record buffer (equal ``B`` on all ranks).  Returns ``(gathered, work)``
+    with ``gathered`` of shape ``[world, WORDS_PER_PAIR * B]``; ``split_gathered`` gives per-rank views."""
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty((world, flat.numel()), dtype=flat.dtype, device=flat.device)
+    if flat.is_cuda:
+        work = dist.all_gather_into_tensor(out.view(-1), flat, group=group, async_op=async_op)
+    else:   # gloo has no all_gather_into_tensor for CPU tensors on every version: use the list form
+        work = dist.all_gather(list(out.unbind(0)), flat, group=group, async_op=async_op)
+    return out, work
+
+
+def split_gathered(gathered: torch.Tensor, B: int) -> list[BatchResult]:
+    return [packed_views(gathered[r], B) for r in range(gathered.shape[0])]
+
+
+def sharded_solve(solve_local, n_pairs: int, rank: int, world: int, device, group=None):
+    """Solve ``n_pairs`` pairs split over ``world`` ranks and return every rank's results.
+
+    ``solve_local(lo, hi, out: BatchResult)`` must fill ``out`` for global pairs ``[lo, hi)``.  Ranks
+    are padded to the largest shard so one fixed-size all-gather suffices; returns a list of
+    ``(lo, hi, BatchResult)`` in rank order (views into the gathered buffer)."""
+    bounds = [shard_bounds(n_pairs, r, world) for r in range(world)]
+    Bmax = max(hi - lo for lo, hi in bounds)
+    flat, views = alloc_packed(Bmax, device)
+    flat.zero_()
+    lo, hi = bounds[rank]
+    n = hi - lo
+    local = BatchResult(alpha=views.alpha[:n], contact=views.contact[:n], grad=views.grad[:n],
+                        iters=views.iters[:n], status=views.status[:n])
+    solve_local(lo, hi, local)
+    if world == 1:
+        return [(lo, hi, local)]
+    gathered, _ = all_gather_packed(flat, Bmax, world, group=group)
+    outs = []
+    for r, (rlo, rhi) in enumerate(bounds):
+        v = packed_views(gathered[r], Bmax)
+        k = rhi - rlo
+        outs.append((rlo, rhi, BatchResult(alpha=v.alpha[:k], contact=v.contact[:k], grad=v.grad[:k],
+                                           iters=v.iters[:k], status=v.status[:k])))
+    return outs

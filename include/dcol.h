@@ -29,6 +29,7 @@
 #ifndef DCOL_H_
 #define DCOL_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -124,12 +125,18 @@ int dcol_proximity_batch_device(const dcol_plan* plan, const double* d_pose1, co
                                 int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact,
                                 double* d_grad, int32_t* d_iters, int32_t* d_status, void* stream);
 
-/* Same computation with HOST buffers: allocates device scratch, copies in, plans, solves,
- * copies out, synchronises.  This is the call a reference-side binding makes. */
+/* Same computation with HOST buffers: the batch flows in chunks through copy-in, plan + solve and
+ * copy-out streams (device scratch cached in the table), then the call synchronises.  This is the
+ * call a reference-side binding makes.  Calls on one table are serialised. */
 int dcol_proximity_batch_host(const dcol_shape_table* table, const int32_t* idx1, const int32_t* idx2,
                               const double* pose1, const double* pose2, int64_t B, double tol, int32_t max_iter,
                               uint32_t flags, double* alpha, double* contact, double* grad, int32_t* iters,
                               int32_t* status);
+
+/* Page-locked host memory for the buffers handed to dcol_proximity_batch_host (pageable memory
+ * works too, but its copies are staged and do not overlap the solve). */
+int  dcol_host_alloc(size_t bytes, void** out);
+void dcol_host_free(void* p);
 
 /* Debug aid: solve ONE pair and also return the per-iteration mu = s'z/deg trace
  * (mu_trace[DCOL_MAX_ITER + 1], NaN padded) and the final (x[8], s[72], z[72]).  Host pointers. */

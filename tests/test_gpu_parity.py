@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the C ABI) with the reference goldens and with the oracle.
+
+Bars (BASELINE.json north_star): alpha within 1e-8 relative (absolute floor 1e-8 for |alpha| < 1),
+gradients within 1e-6 norm-relative, identical PDIP iteration counts and status words.  The
+committed goldens were produced by the unmodified Python reference (oracle/gen_golden.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+ALPHA_RTOL = 1e-8
+GRAD_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def dcol():
+    import dcol_trajectory_optimization_b200 as d
+    return d
+
+
+def _solve_golden(dcol, g):
+    eng = dcol.ProximityEngine((g["shape_records"], g["A"], g["b"]))
+    B = len(g["idx1"])
+    out = dict(alpha=np.empty(B), iters=np.empty(B, np.int32), status=np.empty(B, np.int32),
+               grad=np.empty((B, 12)), contact=np.empty((B, 3)))
+    for tol in np.unique(g["tol"]):
+        sel = np.where(g["tol"] == tol)[0]
+        r = eng.solve_host(g["idx1"][sel], g["idx2"][sel], g["pose1"][sel], g["pose2"][sel], tol=float(tol))
+        for k in out:
+            out[k][sel] = getattr(r, k)
+    eng.close()
+    return out
+
+
+def _alpha_err(a, ref):
+    return np.abs(a - ref) / np.maximum(np.abs(ref), 1.0)
+
+
+def _grad_err(g, ref):
+    return np.abs(g - ref).max(axis=1) / np.abs(ref).max(axis=1)
+
+
+def _mu_ties(g, rel=1e-9):
+    """Pairs whose reference mu trace touches the tolerance to rounding: `mu < tol` is then decided by
+    the last bit (e.g. coincident spheres give mu = 0.01^k exactly) and the count may differ by one."""
+    mu, tol = g["mu"], g["tol"][:, None]
+    with np.errstate(invalid="ignore"):
+        return (np.abs(mu - tol) <= rel * tol).any(axis=1)
+
+
+@pytest.mark.parametrize("name", ["scenarios", "config4_sample", "config5_sample"])
+def test_golden_parity(dcol, name):
+    g = load_golden(name)
+    out = _solve_golden(dcol, g)
+    assert np.array_equal(out["status"], g["status"])
+    assert np.array_equal(out["iters"], g["iters"])
+    assert _alpha_err(out["alpha"], g["alpha"]).max() < ALPHA_RTOL
+    assert _grad_err(out["grad"], g["grad"]).max() < GRAD_RTOL
+    scale = np.maximum(np.abs(g["x"][:, :3]).max(axis=1), 1.0)
+    assert (np.abs(out["contact"] - g["x"][:, :3]).max(axis=1) / scale).max() < 1e-7
+
+
+def test_edge_cases(dcol):
+    """Unsupported pairs, NaN/Inf inputs, separations to 1e6, coincident centres, tolerances from
+    1e-2 to 1e-12, body-frame offsets, irregular polygons (the diag-only triangular solve), 14-face
+    polytope (runtime face count)."""
+    g = load_golden("edge_cases")
+    out = _solve_golden(dcol, g)
+    tag = np.array([str(t) for t in g["tag"]])
+    stable = ~np.isin(tag, ["tol0", "sep1e+09"]) & ~_mu_ties(g)
+    assert stable.sum() > 600
+    assert np.array_equal(out["status"][stable], g["status"][stable])
+    assert np.array_equal(out["iters"][stable], g["iters"][stable])
+    assert np.all(out["status"][tag == "case4"] == 4)
+    assert np.all(out["status"][np.isin(tag, ["nan_r", "nan_p", "inf_r"])] == 2)
+    assert np.all(out["status"][tag == "tol0"] != 0)
+    ok = stable & (g["status"] == 0)
+    assert _alpha_err(out["alpha"][ok], g["alpha"][ok]).max() < ALPHA_RTOL
+    assert np.all(np.isnan(out["alpha"][out["status"] != 0]))
+    well = ok & np.isin(tag, ["offset", "shape7", "shape8", "shape9", "sep100", "tol0.01", "tol1e-09"])
+    assert _grad_err(out["grad"][well], g["grad"][well]).max() < GRAD_RTOL
+    # ties: alpha still agrees to the absolute floor even if the count differs by one
+    ties = _mu_ties(g) & (g["status"] == 0)
+    assert np.all(np.abs(out["iters"][ties] - g["iters"][ties]) <= 1)
+    assert _alpha_err(out["alpha"][ties], g["alpha"][ties]).max() < 1e-6
+
+
+@pytest.mark.parametrize("workload", ["config4", "config5"])
+def test_large_random_vs_oracle(dcol, oracle, workload):
+    """200k seeded pairs per workload against the CPU oracle (which is pinned to the reference).
+    Iteration counts are compared pair by pair; at this size a flip is a bug, not a tie."""
+    from dcol_trajectory_optimization_b200 import workloads as W
+    from dcol_trajectory_optimization_b200.shapes import flatten_shapes
+    if workload == "config4":
+        shapes, i1, i2, p1, p2 = W.config4_batch(200_000, seed=4321)
+    else:
+        shapes, i1, i2, p1, p2 = W.config5_batch(n_obs=128, n_knots=50, n_cand=32, seed=7)
+    rec, A, b = flatten_shapes(shapes)
+    ref = oracle.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=oracle.GRAD_EXACT)
+    eng = dcol.ProximityEngine((rec, A, b))
+    res = eng.solve_host(i1, i2, p1, p2)
+    eng.close()
+    assert np.array_equal(res.status, ref["status"])
+    n_flip = int((res.iters != ref["iters"]).sum())
+    assert n_flip == 0, f"{n_flip} iteration-count mismatches of {len(i1)}"
+    ok = ref["status"] == 0
+    assert _alpha_err(res.alpha[ok], ref["alpha"][ok]).max() < ALPHA_RTOL
+    assert _grad_err(res.grad[ok], ref["grad"][ok]).max() < GRAD_RTOL
+    scale = np.maximum(np.abs(ref["contact"][ok]).max(axis=1), 1.0)
+    assert (np.abs(res.contact[ok] - ref["contact"][ok]).max(axis=1) / scale).max() < 1e-7
+
+
+def test_device_api_matches_host_api_and_plan_reuse(dcol):
+    import torch
+    from dcol_trajectory_optimization_b200 import workloads as W
+    shapes, i1, i2, p1, p2 = W.config4_batch(10_007, seed=11)   # ragged: not a multiple of the CTA size
+    eng = dcol.ProximityEngine(shapes)
+    host = eng.solve_host(i1, i2, p1, p2)
+    plan = eng.plan(i1, i2)
+    assert plan.size == 10_007 and plan.n_groups == 40
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    dev = eng.solve(plan, d1, d2)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.status.cpu().numpy(), host.status)
+    assert np.array_equal(dev.iters.cpu().numpy(), host.iters)
+    assert np.array_equal(dev.alpha.cpu().numpy(), host.alpha)
+    assert np.array_equal(dev.grad.cpu().numpy(), host.grad)
+    # same plan, new poses (what ALTRO does every iteration)
+    d1b = d1.clone()
+    d1b[:, :3] += 0.05
+    dev2 = eng.solve(plan, d1b, d2, want_grad=False, want_contact=False)
+    host2 = eng.solve_host(i1, i2, d1b.cpu().numpy(), p2, want_grad=False, want_contact=False)
+    torch.cuda.synchronize()
+    assert dev2.grad is None and dev2.contact is None
+    assert np.array_equal(dev2.alpha.cpu().numpy(), host2.alpha)
+    plan.close()
+    eng.close()
+
+
+def test_empty_and_single(dcol):
+    import torch
+    eng = dcol.ProximityEngine([dcol.SphereMRP(0.5), dcol.SphereMRP(0.25)])
+    r = eng.solve_host(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 6)), np.zeros((0, 6)))
+    assert r.alpha.shape == (0,) and r.grad.shape == (0, 12)
+    plan = eng.plan(torch.zeros(0, dtype=torch.int32), torch.zeros(0, dtype=torch.int32))
+    out = eng.solve(plan, torch.zeros((0, 6), dtype=torch.float64, device="cuda"),
+                    torch.zeros((0, 6), dtype=torch.float64, device="cuda"))
+    assert out.alpha.numel() == 0
+    # sphere-sphere closed form: alpha* = |r2 - r1| / (R1 + R2); PDIP stops at mu < 1e-6 (<= 3e-5 away)
+    p1 = np.array([[0.1, -0.2, 0.3, 0.0, 0.0, 0.0]])
+    p2 = np.array([[3.0, 1.0, -0.5, 0.1, 0.2, 0.3]])
+    r = eng.solve_host([0], [1], p1, p2)
+    exact = np.linalg.norm(p2[0, :3] - p1[0, :3]) / 0.75
+    assert r.status[0] == 0 and abs(r.alpha[0] - exact) / exact < 3e-5
+    with pytest.raises(dcol.engine._lib.DcolError):
+        eng.solve_host([0], [2], p1, p2)          # shape index out of range
+    eng.close()
+
+
+def test_scalar_drop_in_api(dcol):
+    """proximity_mrp / proximity_gradient with the reference's signatures on the scenario KATs
+    (SURVEY.md appendix C), built from primitive objects exactly as systems/*.py build them."""
+    from dcol_trajectory_optimization_b200.proximity import proximity_gradient, proximity_mrp
+    vic = dcol.create_rect_prism(2.5, 0.15, 0.01)
+    vic.r, vic.p = [1.5, 1.5, 0.0], [0.0, 0.0, 0.0]          # lists, as piano_mover.py:176-178 assigns them
+    obs = dcol.create_rect_prism(3.0, 3.0, 1.0)
+    obs.r = np.array([1.5, 3.5, 0.0])
+    alpha, x = proximity_mrp(vic, obs)
+    assert isinstance(alpha, np.float64) and x.shape == (3,)
+    assert abs(alpha - 1.2698416034604294) < 1e-8 * alpha
+    alpha2, g = proximity_gradient(vic, obs, pdip_tol=1e-6, verbose=False)
+    assert alpha2 == alpha and g.shape == (12,)
+    ref_g = np.array([0, -0.63491674459100977, 0, 0, 0, 0, 0, 0.63491674459089609, 0, 0, 0, 0])
+    assert np.abs(g - ref_g).max() < 1e-6 * np.abs(ref_g).max()
+    s1, s2 = dcol.SphereMRP(0.25), dcol.SphereMRP(0.8)
+    s1.r, s2.r = np.array([-8.0, 0.0, 4.0]), np.array([-3.0, 1.0, 5.5])
+    a, _ = proximity_mrp(s1, s2)
+    assert abs(a - np.linalg.norm(s2.r - s1.r) / 1.05) / a < 3e-5
+    # error convention: the reference raises, it never returns flags
+    with pytest.raises(ValueError):
+        proximity_mrp(dcol.CapsuleMRP(0.3, 1.2), dcol.CylinderMRP(0.4, 1.5))     # np.vstack ValueError
+    s1.r = np.array([np.nan, 0.0, 0.0])
+    with pytest.raises(ValueError):
+        proximity_gradient(s1, s2)                                               # check_finite ValueError
+    s1.r = np.array([-8.0, 0.0, 4.0])
+    with pytest.raises(Exception, match="Maximum number of iterations"):
+        proximity_mrp(s1, obs, pdip_tol=0.0)
+
+
+def test_debug_trace_matches_reference_mu_trace(dcol):
+    g = load_golden("scenarios")
+    eng = dcol.ProximityEngine((g["shape_records"], g["A"], g["b"]))
+    for k in range(len(g["idx1"])):
+        r = eng.trace_pair(g["idx1"][k], g["idx2"][k], g["pose1"][k], g["pose2"][k])
+        n, m, it = int(g["n"][k]), int(g["m"][k]), int(g["iters"][k])
+        assert (r["n"], r["m"], r["iters"], r["status"]) == (n, m, it, 0)
+        np.testing.assert_allclose(r["mu"][:it + 1], g["mu"][k, :it + 1], rtol=1e-5)
+        np.testing.assert_allclose(r["x"], g["x"][k, :n], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(r["s"], g["s"][k, :m], rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(r["z"], g["z"][k, :m], rtol=1e-7, atol=1e-10)
+    eng.close()
+
+
+def test_full_size_properties(dcol):
+    """Size-independent checks at a BASELINE-size batch (2^22 pairs, config 4), where the oracle is
+    too slow to be the checker: every pair converges; translating both primitives leaves alpha
+    unchanged; the position gradients of the two primitives cancel (translation invariance of the
+    Lagrangian, to the dual residual the reference leaves at mu < tol); sphere-sphere pairs hit
+    their closed form."""
+    import torch
+    from dcol_trajectory_optimization_b200 import workloads as W
+    B = 1 << 22
+    shapes, i1, i2, p1, p2 = W.config4_batch(B, seed=2024)
+    eng = dcol.ProximityEngine(shapes)
+    plan = eng.plan(i1, i2)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    r = eng.solve(plan, d1, d2)
+    torch.cuda.synchronize()
+    assert int((r.status != 0).sum()) == 0
+    it = r.iters.cpu().numpy()
+    assert 4 <= it.min() and it.max() <= 30 and 7.5 < it.mean() < 8.6
+    g = r.grad
+    cancel = (g[:, 0:3] + g[:, 6:9]).abs().max(dim=1).values / g.abs().max(dim=1).values
+    assert float(cancel.max()) < 1e-4 and float(cancel.median()) < 1e-9
+    shift = torch.tensor([0.7, -1.3, 2.1, 0, 0, 0], dtype=torch.float64, device="cuda")
+    r2 = eng.solve(plan, d1 + shift, d2 + shift, want_grad=False, want_contact=False)
+    torch.cuda.synchronize()
+    same = (r2.iters == r.iters)
+    rel = ((r2.alpha - r.alpha).abs() / r.alpha.abs().clamp(min=1.0))[same]
+    assert float(same.double().mean()) > 0.999 and float(rel.max()) < 1e-8
+    ss = torch.from_numpy((i1 == 5) & (i2 == 5)).cuda()
+    exact = (d2[ss, :3] - d1[ss, :3]).norm(dim=1) / 1.0
+    assert float(((r.alpha[ss] - exact).abs() / exact).max()) < 3e-5
+    plan.close()
+    eng.close()
