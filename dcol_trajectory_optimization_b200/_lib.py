@@ -11,7 +11,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdcol_b200.so")
+LIB_PATH = os.environ.get("DCOL_LIB") or os.path.join(HERE, "libdcol_b200.so")   # DCOL_LIB: build experiments
 CSRC = os.path.join(HERE, "csrc")
 
 WANT_CONTACT, WANT_GRAD = 1, 2

@@ -6,6 +6,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -59,6 +60,9 @@ struct HostScratch {
 
 } /* namespace */
 
+struct dcol_plan;
+extern "C" void dcol_plan_destroy(dcol_plan* P);
+
 struct dcol_shape_table {
     int device;
     std::vector<dcol_shape> shapes;
@@ -67,14 +71,18 @@ struct dcol_shape_table {
     /* host entry point state */
     std::mutex mu;
     HostScratch scratch[2];
-    cudaStream_t streams[3] = { nullptr, nullptr, nullptr }; /* h2d, compute, d2h */
-    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+    dcol_plan* plans[2] = { nullptr, nullptr };
+    cudaStream_t streams[4] = { nullptr, nullptr, nullptr, nullptr }; /* h2d, plan, solve, d2h */
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_plan[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr },
+                ev_out[2] = { nullptr, nullptr };
 };
 
 struct dcol_plan {
     const dcol_shape_table* table;
-    int64_t B;
-    int32_t* d_perm;
+    int64_t B, capacity;
+    int32_t* d_perm;   /* [capacity] plan order -> pair index             */
+    int32_t* d_counts; /* [n_shapes^2 + 1] histogram / cursor + error flag */
+    std::vector<int32_t> h_counts;
     std::vector<Group> groups;
     int32_t n_launches;
 };
@@ -273,13 +281,79 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
     cudaSetDevice(T->device);
     for (int i = 0; i < 2; ++i) {
         T->scratch[i].release();
+        dcol_plan_destroy(T->plans[i]);
         if (T->ev_in[i]) cudaEventDestroy(T->ev_in[i]);
+        if (T->ev_plan[i]) cudaEventDestroy(T->ev_plan[i]);
         if (T->ev_done[i]) cudaEventDestroy(T->ev_done[i]);
         if (T->ev_out[i]) cudaEventDestroy(T->ev_out[i]);
     }
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
         if (T->streams[i]) cudaStreamDestroy(T->streams[i]);
     delete T;
+}
+
+/* Builds the grouping of B pairs into a plan whose device buffers (counts: n_keys + 1 ints, perm: B ints)
+ * already exist.  Synchronises `stream` once, after the histogram, to read the group sizes; the scatter
+ * is left in flight on `stream`. */
+static int plan_build(dcol_plan* P, const int32_t* d_idx1, const int32_t* d_idx2, int64_t B, cudaStream_t stream)
+{
+    const dcol_shape_table* T = P->table;
+    const int32_t ns = (int32_t)T->shapes.size();
+    const int32_t nk = ns * ns;
+    P->B = B;
+    P->groups.clear();
+    P->n_launches = 0;
+    if (B == 0) return 0;
+    (void)cudaGetLastError(); /* drop a stale error left by another library in this process */
+    const unsigned blocks = (unsigned)((B + kPlanTile - 1) / kPlanTile);
+    P->h_counts.resize((size_t)nk + 1);
+    DCOL_CUDA(cudaMemsetAsync(P->d_counts, 0, sizeof(int32_t) * ((size_t)nk + 1), stream));
+    plan_histogram<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, P->d_counts, P->d_counts + nk);
+    DCOL_CUDA(cudaGetLastError());
+    DCOL_CUDA(cudaMemcpyAsync(P->h_counts.data(), P->d_counts, sizeof(int32_t) * ((size_t)nk + 1), cudaMemcpyDeviceToHost, stream));
+    DCOL_CUDA(cudaStreamSynchronize(stream));
+    if (P->h_counts[nk] != 0) return fail(DCOL_E_INDEX, "shape index out of range");
+    int64_t off = 0;
+    for (int32_t key = 0; key < nk; ++key) {
+        const int32_t cnt = P->h_counts[key];
+        P->h_counts[key] = (int32_t)off; /* becomes the scatter cursor */
+        if (cnt == 0) continue;
+        Group g;
+        g.i1 = key / ns;
+        g.i2 = key % ns;
+        g.first = off;
+        g.count = cnt;
+        g.supported = class_pair_supported(T->cls[g.i1], T->cls[g.i2]);
+        P->groups.push_back(g);
+        off += cnt;
+    }
+    P->n_launches = (int32_t)P->groups.size();
+    /* h_counts lives in the plan, so the (pageable, staged) copy may complete after we return */
+    DCOL_CUDA(cudaMemcpyAsync(P->d_counts, P->h_counts.data(), sizeof(int32_t) * (size_t)nk, cudaMemcpyHostToDevice, stream));
+    plan_scatter<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, P->d_counts, P->d_perm);
+    DCOL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int plan_alloc(const dcol_shape_table* T, int64_t capacity, dcol_plan** out)
+{
+    const int32_t ns = (int32_t)T->shapes.size();
+    dcol_plan* P = new dcol_plan();
+    P->table = T;
+    P->B = 0;
+    P->capacity = capacity;
+    P->d_perm = nullptr;
+    P->d_counts = nullptr;
+    P->n_launches = 0;
+    cudaError_t e = cudaMalloc(&P->d_counts, sizeof(int32_t) * ((size_t)ns * ns + 1));
+    if (e == cudaSuccess && capacity > 0) e = cudaMalloc(&P->d_perm, sizeof(int32_t) * (size_t)capacity);
+    if (e != cudaSuccess) {
+        cudaFree(P->d_counts);
+        delete P;
+        return fail_cuda(e, "plan allocation");
+    }
+    *out = P;
+    return 0;
 }
 
 int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int32_t* d_idx2, int64_t B, void* stream_,
@@ -287,64 +361,14 @@ int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int
 {
     if (!T || !out || B < 0 || (B > 0 && (!d_idx1 || !d_idx2))) return fail(DCOL_E_ARG, "dcol_plan_create: bad argument");
     if (B > 0x7fffffffLL) return fail(DCOL_E_ARG, "dcol_plan_create: at most 2^31-1 pairs per plan");
-    cudaStream_t stream = (cudaStream_t)stream_;
     DCOL_CUDA(cudaSetDevice(T->device));
-    dcol_plan* P = new dcol_plan();
-    P->table = T;
-    P->B = B;
-    P->d_perm = nullptr;
-    P->n_launches = 0;
-    if (B == 0) {
-        *out = P;
-        return 0;
-    }
-    const int32_t ns = (int32_t)T->shapes.size();
-    const int32_t nk = ns * ns;
-    int32_t* d_counts = nullptr;
-    cudaError_t e = cudaMalloc(&d_counts, sizeof(int32_t) * ((size_t)nk + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&P->d_perm, sizeof(int32_t) * (size_t)B);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * ((size_t)nk + 1), stream);
-    const unsigned blocks = (unsigned)((B + kPlanTile - 1) / kPlanTile);
-    std::vector<int32_t> counts((size_t)nk + 1);
-    if (e == cudaSuccess) {
-        plan_histogram<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, d_counts, d_counts + nk);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), d_counts, sizeof(int32_t) * ((size_t)nk + 1), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess || counts[nk] != 0) {
-        cudaFree(d_counts);
-        cudaFree(P->d_perm);
-        delete P;
-        if (e != cudaSuccess) return fail_cuda(e, "dcol_plan_create");
-        return fail(DCOL_E_INDEX, "dcol_plan_create: shape index out of range");
-    }
-    std::vector<int32_t> cursor((size_t)nk, 0);
-    int64_t off = 0;
-    for (int32_t key = 0; key < nk; ++key) {
-        cursor[key] = (int32_t)off;
-        if (counts[key] == 0) continue;
-        Group g;
-        g.i1 = key / ns;
-        g.i2 = key % ns;
-        g.first = off;
-        g.count = counts[key];
-        g.supported = class_pair_supported(T->cls[g.i1], T->cls[g.i2]);
-        P->groups.push_back(g);
-        off += counts[key];
-    }
-    P->n_launches = (int32_t)P->groups.size();
-    e = cudaMemcpyAsync(d_counts, cursor.data(), sizeof(int32_t) * (size_t)nk, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) {
-        plan_scatter<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, d_counts, P->d_perm);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream); /* cursor is host memory about to go away */
-    cudaFree(d_counts);
-    if (e != cudaSuccess) {
-        cudaFree(P->d_perm);
-        delete P;
-        return fail_cuda(e, "dcol_plan_create");
+    dcol_plan* P = nullptr;
+    int rc = plan_alloc(T, B, &P);
+    if (rc) return rc;
+    rc = plan_build(P, d_idx1, d_idx2, B, (cudaStream_t)stream_);
+    if (rc) {
+        dcol_plan_destroy(P);
+        return rc;
     }
     *out = P;
     return 0;
@@ -353,10 +377,9 @@ int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int
 void dcol_plan_destroy(dcol_plan* P)
 {
     if (!P) return;
-    if (P->d_perm) {
-        cudaSetDevice(P->table->device);
-        cudaFree(P->d_perm);
-    }
+    cudaSetDevice(P->table->device);
+    cudaFree(P->d_perm);
+    cudaFree(P->d_counts);
     delete P;
 }
 int64_t dcol_plan_size(const dcol_plan* P) { return P ? P->B : 0; }
@@ -376,6 +399,7 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
         return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null buffer");
     cudaStream_t stream = (cudaStream_t)stream_;
     DCOL_CUDA(cudaSetDevice(P->table->device));
+    (void)cudaGetLastError(); /* drop a stale error left by another library in this process */
     for (const Group& g : P->groups) {
         BatchArgs a = { P->d_perm, g.first, g.count, d_pose1, d_pose2, tol, max_iter, flags,
                         d_alpha, d_contact, d_grad, d_iters, d_status, nullptr };
@@ -406,19 +430,23 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         return fail(DCOL_E_ARG, "dcol_proximity_batch_host: null buffer");
     std::lock_guard<std::mutex> lock(T->mu);
     DCOL_CUDA(cudaSetDevice(T->device));
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
         if (!T->streams[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         if (!T->ev_in[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_in[i], cudaEventDisableTiming));
+        if (!T->ev_plan[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_plan[i], cudaEventDisableTiming));
         if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
         if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
     }
-    const int64_t kChunk = 1 << 20;
+    int64_t kChunk = 1 << 20;
+    if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
     for (int i = 0; i < 2; ++i) {
         HostScratch& S = T->scratch[i];
         if (S.cap >= chunk) continue;
         S.release();
+        dcol_plan_destroy(T->plans[i]);
+        T->plans[i] = nullptr;
         DCOL_CUDA(cudaMalloc(&S.idx1, sizeof(int32_t) * chunk));
         DCOL_CUDA(cudaMalloc(&S.idx2, sizeof(int32_t) * chunk));
         DCOL_CUDA(cudaMalloc(&S.iters, sizeof(int32_t) * chunk));
@@ -429,51 +457,55 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         DCOL_CUDA(cudaMalloc(&S.contact, sizeof(double) * 3 * chunk));
         DCOL_CUDA(cudaMalloc(&S.grad, sizeof(double) * 12 * chunk));
         S.cap = chunk;
+        int rc0 = plan_alloc(T, chunk, &T->plans[i]);
+        if (rc0) return rc0;
     }
-    cudaStream_t s_in = T->streams[0], s_run = T->streams[1], s_out = T->streams[2];
+    /* Four streams: copy-in, plan (counting sort), solve, copy-out.  The only host wait per chunk is for
+     * that chunk's own histogram, so chunk i+1 is copied in and planned while chunk i is being solved and
+     * chunk i-1 is being copied out. */
+    cudaStream_t s_in = T->streams[0], s_plan = T->streams[1], s_run = T->streams[2], s_out = T->streams[3];
     int rc = 0;
-    dcol_plan* plans[2] = { nullptr, nullptr };
-    int64_t n_chunks = (B + chunk - 1) / chunk;
+    const int64_t n_chunks = (B + chunk - 1) / chunk;
     for (int64_t ci = 0; ci < n_chunks && rc == 0; ++ci) {
         const int slot = (int)(ci & 1);
         HostScratch& S = T->scratch[slot];
+        dcol_plan* P = T->plans[slot];
         const int64_t k0 = ci * chunk, n = std::min(chunk, B - k0);
         if (ci >= 2) {
-            /* the slot's previous outputs must have left the device, its inputs must have been consumed */
-            DCOL_CUDA(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));
-            DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));
+            DCOL_CUDA(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));  /* inputs + perm consumed by the solve   */
+            DCOL_CUDA(cudaStreamWaitEvent(s_plan, T->ev_done[slot], 0));
+            DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));  /* previous outputs have left the device */
         }
         DCOL_CUDA(cudaMemcpyAsync(S.idx1, idx1 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
         DCOL_CUDA(cudaMemcpyAsync(S.idx2, idx2 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA(cudaEventRecord(T->ev_in[slot], s_in));
         DCOL_CUDA(cudaMemcpyAsync(S.pose1, pose1 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
         DCOL_CUDA(cudaMemcpyAsync(S.pose2, pose2 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
-        DCOL_CUDA(cudaEventRecord(T->ev_in[slot], s_in));
-        DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
-        /* the slot's previous plan: its solve finished before the last plan_create returned (same stream) */
-        dcol_plan_destroy(plans[slot]);
-        plans[slot] = nullptr;
-        rc = dcol_plan_create(T, S.idx1, S.idx2, n, s_run, &plans[slot]);
+        DCOL_CUDA(cudaStreamWaitEvent(s_plan, T->ev_in[slot], 0));
+        rc = plan_build(P, S.idx1, S.idx2, n, s_plan);
         if (rc) break;
-        dcol_plan* P = plans[slot];
+        DCOL_CUDA(cudaEventRecord(T->ev_plan[slot], s_plan));
+        DCOL_CUDA(cudaEventRecord(T->ev_in[slot], s_in)); /* now also covers the poses */
+        DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_plan[slot], 0));
+        DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
         rc = dcol_proximity_batch_device(P, S.pose1, S.pose2, tol, max_iter, flags, S.alpha, S.contact, S.grad, S.iters,
                                          S.status, s_run);
-        cudaError_t e = cudaEventRecord(T->ev_done[slot], s_run);
-        if (rc == 0 && e == cudaSuccess) e = cudaStreamWaitEvent(s_out, T->ev_done[slot], 0);
-        if (rc == 0 && e == cudaSuccess) e = cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out);
-        if (rc == 0 && e == cudaSuccess) e = cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out);
-        if (rc == 0 && e == cudaSuccess) e = cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out);
-        if (rc == 0 && e == cudaSuccess && (flags & DCOL_WANT_CONTACT))
-            e = cudaMemcpyAsync(contact + 3 * k0, S.contact, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s_out);
-        if (rc == 0 && e == cudaSuccess && (flags & DCOL_WANT_GRAD))
-            e = cudaMemcpyAsync(grad + 12 * k0, S.grad, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, s_out);
-        if (e == cudaSuccess) e = cudaEventRecord(T->ev_out[slot], s_out);
-        if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_batch_host");
+        if (rc) break;
+        DCOL_CUDA(cudaEventRecord(T->ev_done[slot], s_run));
+        DCOL_CUDA(cudaStreamWaitEvent(s_out, T->ev_done[slot], 0));
+        DCOL_CUDA(cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA(cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA(cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
+        if (flags & DCOL_WANT_CONTACT)
+            DCOL_CUDA(cudaMemcpyAsync(contact + 3 * k0, S.contact, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s_out));
+        if (flags & DCOL_WANT_GRAD)
+            DCOL_CUDA(cudaMemcpyAsync(grad + 12 * k0, S.grad, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA(cudaEventRecord(T->ev_out[slot], s_out));
     }
     cudaError_t e = cudaStreamSynchronize(s_out);
     cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_plan);
     cudaStreamSynchronize(s_run);
-    dcol_plan_destroy(plans[0]);
-    dcol_plan_destroy(plans[1]);
     if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_batch_host");
     return rc;
 }

@@ -18,7 +18,14 @@
 
 namespace dcol {
 
-constexpr int kThreads = 64; /* threads per CTA: register-heavy FP64 code, 4+ CTAs per SM */
+#ifndef DCOL_THREADS
+#define DCOL_THREADS 64
+#endif
+#ifndef DCOL_MIN_BLOCKS
+#define DCOL_MIN_BLOCKS 4
+#endif
+constexpr int kThreads = DCOL_THREADS;      /* threads per CTA                                        */
+constexpr int kMinBlocks = DCOL_MIN_BLOCKS; /* CTAs per SM the register allocation must leave room for */
 
 /* everything of a launch that does not depend on the specialisation */
 struct BatchArgs {
@@ -51,7 +58,7 @@ struct GroupArgs {
 };
 
 template <class P1, class P2>
-__global__ void __launch_bounds__(kThreads) pair_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
 {
     typedef Solver<P1, P2> S;
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;

@@ -55,15 +55,35 @@ namespace dcol {
 /* ---------------------------------------------------------------------------------------- */
 /* scalar helpers                                                                            */
 
+/* 1/sqrt(x) and 1/x for the solver's scalars (products s_i z_i, Cholesky pivots, cone determinants).
+ * On the device: the MUFU seed (rsqrt/rcp.approx.f64, ~2^-22 relative) and ONE third-order Newton step,
+ *   e = 1 - x y^2,  y += y e (1/2 + 3/8 e)        |      e = 1 - x y,  y += y (e + e^2),
+ * which brings the error to ~e^3 < 2^-60, i.e. rounding level, in 5 (resp. 3) FP64 instructions with no
+ * branch; the CUDA library routines spend ~4x that on denormal / special-case paths this solver never
+ * needs: a zero, negative, infinite or NaN argument still yields a non-finite result, which is all the
+ * status logic relies on. */
 DCOL_HD double rsqrt_(double x)
 {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
 #else
     return 1.0 / sqrt(x);
 #endif
 }
-DCOL_HD double rcp_(double x) { return 1.0 / x; }
+DCOL_HD double rcp_(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+#else
+    return 1.0 / x;
+#endif
+}
 DCOL_HD double max_(double a, double b) { return (b > a) ? b : a; } /* Python max(a, b): keeps a on NaN */
 DCOL_HD double min_(double a, double b) { return (b < a) ? b : a; }
 /* 0 if x is finite, NaN otherwise (x * 0 is NaN for inf and NaN) */
@@ -75,7 +95,7 @@ DCOL_HD void dcm_from_mrp(const double p[3], double Q[3][3])
 {
     const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
     const double t = 1.0 + pp;
-    const double iden = 1.0 / (t * t);
+    const double iden = rcp_(t * t);
     const double k8 = 8.0 * iden, k4 = 4.0 * (1.0 - pp) * iden;
     Q[0][0] = 1.0 - k8 * (p[1] * p[1] + p[2] * p[2]);
     Q[1][1] = 1.0 - k8 * (p[0] * p[0] + p[2] * p[2]);
@@ -94,7 +114,7 @@ DCOL_HD void dcm_from_mrp(const double p[3], double Q[3][3])
 DCOL_HD void dcm_derivative_contract(const double p[3], const double Q[3][3], const double M[3][3], double out[3])
 {
     const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
-    const double t = 1.0 + pp, iD = 1.0 / (t * t);
+    const double t = 1.0 + pp, iD = rcp_(t * t);
     const double S[3][3] = { { 0.0, -p[2], p[1] }, { p[2], 0.0, -p[0] }, { -p[1], p[0], 0.0 } };
     DCOL_UNROLL
     for (int k = 0; k < 3; ++k) {
@@ -491,7 +511,8 @@ struct Solver {
             double d = M[j][j];
             DCOL_UNROLL
             for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-            if (d <= 0.0) return j + 1;
+            /* a non-finite entry of M reaches a pivot as NaN (or as +inf, whose rsqrt poisons the solve) */
+            if (!(d > 0.0)) return (d != d) ? DCOL_STATUS_NON_FINITE : DCOL_STATUS_NOT_PD;
             const double ri = rsqrt_(d);
             L[j][j] = d * ri;
             Li[j] = ri;
@@ -522,15 +543,11 @@ struct Solver {
             v[i] = t * Li[i];
         }
     }
-    DCOL_HD static double probe_sym(const double (&M)[N][N], const double (&v)[N])
+    DCOL_HD static double probe_vec(const double (&v)[N])
     {
         double t = 0.0;
         DCOL_UNROLL
-        for (int i = 0; i < N; ++i) {
-            t += nonfinite_probe(v[i]);
-            DCOL_UNROLL
-            for (int j = i; j < N; ++j) t += nonfinite_probe(M[i][j]);
-        }
+        for (int i = 0; i < N; ++i) t += nonfinite_probe(v[i]);
         return t;
     }
 
@@ -620,7 +637,7 @@ struct Solver {
             B.wh[0] = (B.sq[0] * rs + B.zq[0] * rz) * ig;
             DCOL_UNROLL
             for (int i = 1; i < P::Q; ++i) B.wh[i] = -((B.sq[i] * rs - B.zq[i] * rz) * ig);
-            B.bw = 1.0 / (B.wh[0] + 1.0);
+            B.bw = rcp_(B.wh[0] + 1.0);
             /* eta = (J(s)/J(z))^(1/4) */
             const double e2 = (Js * rs) * rz; /* sqrt(Js / Jz) */
             B.ieta = rsqrt_(e2);
@@ -634,7 +651,7 @@ struct Solver {
 
     template <class P>
     DCOL_HD static void pass_a(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&xx)[N],
-                               double (&M)[N][N], double (&rx)[N], double (&va)[N], double (&vl)[N])
+                               double (&M)[N][N], double (&va)[N], double (&vl)[N])
     {
         double ro[P::NOA], rq[P::QA];
         rows<P, true>(p, c, col_e, xx, ro, rq); /* G x - h */
@@ -652,11 +669,10 @@ struct Solver {
             if (P::dyn && i >= no) break;
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;            /* 1 / w_i                       */
-            const double lam = (B.so[i] * B.zo[i]) * ri; /* lambda_i                      */
             const double rho = winv * (B.so[i] + ro[i]); /* (W^-1 rz)_i, rz = s + G x - h */
             B.ta[i] = rho;
             w2[i] = winv * winv;
-            ca[i] = winv * (lam - rho); /* W^-1 b~_affine */
+            ca[i] = -(winv * rho);      /* -W^-2 rz: b~_affine = lambda - rho~, and G~^T lambda = G^T z cancels in bx */
             cl[i] = winv * ri;          /* W^-1 (lambda^-1 o e) */
         }
         P::ort_gram(c, w2, Gl);
@@ -690,24 +706,23 @@ struct Solver {
             P::soc_gram(c, W2, Gl);
             /* shared scalars of lambda: inverse cone product (pdip.py:108-118) and line search (pdip.py:39-47) */
             const double Jl = socJ<P::Q>(B.lam);
-            B.irho = 1.0 / Jl;
-            B.il0 = 1.0 / B.lam[0];
+            B.irho = rcp_(Jl);
+            B.il0 = rcp_(B.lam[0]);
             const double nu = max_(Jl, 1e-25);
             B.ls_isn = rsqrt_(nu);
             B.ls_inu = B.ls_isn * B.ls_isn;
-            B.ls_c0 = 1.0 / (B.lam[0] * B.ls_isn + 1.0);
-            /* W^-1 (lambda - rho~) and W^-1 (lambda^-1 o e), lambda^-1 o e = (lambda_0, -lambda_v) / J(lambda) */
+            B.ls_c0 = rcp_(B.lam[0] * B.ls_isn + 1.0);
+            /* -W^-1 rho~ and W^-1 (lambda^-1 o e), lambda^-1 o e = (lambda_0, -lambda_v) / J(lambda) */
             double t1[P::QA], t2[P::QA];
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
-                t1[i] = B.lam[i] - B.tq[i];
+                t1[i] = -B.tq[i];
                 t2[i] = (i == 0 ? B.lam[i] : -B.lam[i]) * B.irho;
             }
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, t1, B.ieta, qa);
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, t2, B.ieta, ql);
         }
         p.template gram_from_local<N>(Gl, col_e, M);
-        rows_t<P>(p, c, col_e, B.zo, B.zq, rx);
         rows_t<P>(p, c, col_e, ca, qa, va);
         rows_t<P>(p, c, col_e, cl, ql, vl);
     }
@@ -735,7 +750,7 @@ struct Solver {
      * the centring ratio, k = lambda^-1 o (ds~ o dz~) and G~^T k */
     template <class P>
     DCOL_HD static void pass_b(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
-                               double& ts, double& tz, double& d_ls, double& d_lz, double& d_sz, double (&vk)[N])
+                               double (&tm)[2], double& d_l, double& d_sz, double (&vk)[N])
     {
         double ro[P::NOA], rq[P::QA];
         rows<P, false>(p, c, col_e, dx, ro, rq); /* G dx */
@@ -749,10 +764,9 @@ struct Solver {
             const double lam = (B.so[i] * B.zo[i]) * ri;
             const double dz = winv * ro[i] - (lam - B.ta[i]); /* dz~ = G~ dx - b~ */
             const double ds = -lam - dz;                      /* ds~ = d - dz~, d = -lambda */
-            ts = max_(ts, -ds * ri);
-            tz = max_(tz, -dz * ri);
-            d_ls += lam * ds;
-            d_lz += lam * dz;
+            /* both searches run against lambda_i > 0: max(-ds/l, -dz/l) = -min(ds, dz)/l */
+            tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
+            d_l += lam * (ds + dz);
             d_sz += ds * dz;
             const double k = (ds * dz) * ri;
             B.tb[i] = k;
@@ -765,12 +779,11 @@ struct Solver {
             for (int i = 0; i < P::Q; ++i) {
                 dz[i] = g[i] - (B.lam[i] - B.tq[i]);
                 ds[i] = -B.lam[i] - dz[i];
-                d_ls += B.lam[i] * ds[i];
-                d_lz += B.lam[i] * dz[i];
+                d_l += B.lam[i] * (ds[i] + dz[i]);
                 d_sz += ds[i] * dz[i];
             }
-            ts = max_(ts, soc_ls<P>(B, ds));
-            tz = max_(tz, soc_ls<P>(B, dz));
+            tm[0] = max_(tm[0], soc_ls<P>(B, ds));
+            tm[1] = max_(tm[1], soc_ls<P>(B, dz));
             /* w = ds~ o dz~ (pdip.py:165-200); k = lambda^-1 o w (pdip.py:88-122) */
             w[0] = 0.0;
             DCOL_UNROLL
@@ -793,7 +806,7 @@ struct Solver {
      * line-search measures */
     template <class P>
     DCOL_HD static void pass_c(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
-                               double sigmu, double& ts, double& tz)
+                               double sigmu, double (&tm)[2])
     {
         double ro[P::NOA], rq[P::QA];
         rows<P, false>(p, c, col_e, dx, ro, rq);
@@ -808,8 +821,7 @@ struct Solver {
             const double bt = -B.ta[i] - d;               /* b~ = -rho~ - d  */
             const double dz = winv * ro[i] - bt;
             const double ds = d - dz;
-            ts = max_(ts, -ds * ri);
-            tz = max_(tz, -dz * ri);
+            tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
             B.ta[i] = ds;
             B.tb[i] = dz;
         }
@@ -824,8 +836,8 @@ struct Solver {
                 dz[i] = g[i] - bt;
                 ds[i] = d - dz[i];
             }
-            ts = max_(ts, soc_ls<P>(B, ds));
-            tz = max_(tz, soc_ls<P>(B, dz));
+            tm[0] = max_(tm[0], soc_ls<P>(B, ds));
+            tm[1] = max_(tm[1], soc_ls<P>(B, dz));
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
                 B.tq[i] = ds[i];
@@ -928,11 +940,11 @@ struct Solver {
             }
             init_accumulate<P1>(p1, c1, CE1, M, gth);
             init_accumulate<P2>(p2, c2, CE2, M, gth);
-            if (chol(M, L, Li)) return res.status = DCOL_STATUS_NOT_PD;
-            if (probe_sym(M, gth) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
+            if (int bad = chol(M, L, Li)) return res.status = bad; /* numpy cholesky -> LinAlgError; check_finite */
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) x[j] = gth[j];
             chol_solve(L, Li, x); /* x_hat = (G^T G)^-1 G^T h */
+            if (probe_vec(x) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
             rows<P1, true>(p1, c1, CE1, x, b1.so, b1.sq);
             rows<P2, true>(p2, c2, CE2, x, b2.so, b2.sq); /* s~ = G x_hat - h */
             /* solve_triangular(F, -c) reads the UPPER triangle of the lower factor, i.e. its diagonal
@@ -966,46 +978,46 @@ struct Solver {
             if (trace && trace->mu) trace->mu[it] = mu;
             if (mu < tol) return res.status = DCOL_STATUS_OK; /* the only convergence test, pdip.py:418-422 */
 
-            double M[N][N], rx[N], va[N], vl[N];
+            double M[N][N], va[N], vl[N];
             DCOL_UNROLL
             for (int i = 0; i < N; ++i) {
-                rx[i] = (i == 3) ? 1.0 : 0.0; /* + c */
-                va[i] = vl[i] = 0.0;
+                va[i] = (i == 3) ? -1.0 : 0.0; /* -c; pass_a adds -G^T W^-2 rz */
+                vl[i] = 0.0;
                 DCOL_UNROLL
                 for (int j = 0; j < N; ++j) M[i][j] = 0.0;
             }
-            pass_a<P1>(p1, c1, CE1, b1, x, M, rx, va, vl);
-            pass_a<P2>(p2, c2, CE2, b2, x, M, rx, va, vl);
+            pass_a<P1>(p1, c1, CE1, b1, x, M, va, vl);
+            pass_a<P2>(p2, c2, CE2, b2, x, M, va, vl);
             double dx[N];
             DCOL_UNROLL
-            for (int j = 0; j < N; ++j) dx[j] = va[j] - rx[j]; /* bx + G~^T b~ */
-            if (probe_sym(M, dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
-            if (chol(M, L, Li)) return res.status = DCOL_STATUS_NOT_PD;
+            for (int j = 0; j < N; ++j) dx[j] = va[j]; /* bx + G~^T b~ */
+            if (int bad = chol(M, L, Li)) return res.status = bad; /* scipy cholesky: check_finite, LinAlgError */
             chol_solve(L, Li, dx);
+            if (probe_vec(dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
 
             /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
-            double ts = 0.0, tz = 0.0, d_ls = 0.0, d_lz = 0.0, d_sz = 0.0, vk[N];
+            double tm[2] = { 0.0, 0.0 }, d_l = 0.0, d_sz = 0.0, vk[N];
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) vk[j] = 0.0;
-            pass_b<P1>(p1, c1, CE1, b1, dx, ts, tz, d_ls, d_lz, d_sz, vk);
-            pass_b<P2>(p2, c2, CE2, b2, dx, ts, tz, d_ls, d_lz, d_sz, vk);
-            double t = max_(ts, tz);
-            double a = t > 1.0 ? 1.0 / t : 1.0;
-            const double rho = (sz + a * (d_ls + d_lz) + (a * a) * d_sz) / sz;
+            pass_b<P1>(p1, c1, CE1, b1, dx, tm, d_l, d_sz, vk);
+            pass_b<P2>(p2, c2, CE2, b2, dx, tm, d_l, d_sz, vk);
+            double t = max_(tm[0], tm[1]);
+            double a = t > 1.0 ? rcp_(t) : 1.0;
+            const double rho = (sz + a * d_l + (a * a) * d_sz) * rcp_(sz);
             const double cl = max_(0.0, min_(1.0, rho));
             const double sigmu = (cl * cl * cl) * mu;
 
             /* corrector: rhs = rhs_affine + G~^T k - sigma mu G~^T (lambda^-1 o e), same factor   pdip.py:450-460 */
             DCOL_UNROLL
-            for (int j = 0; j < N; ++j) dx[j] = (va[j] - rx[j]) + vk[j] - sigmu * vl[j];
-            if (probe_sym(M, dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
+            for (int j = 0; j < N; ++j) dx[j] = va[j] + vk[j] - sigmu * vl[j];
             chol_solve(L, Li, dx);
-            ts = 0.0;
-            tz = 0.0;
-            pass_c<P1>(p1, c1, CE1, b1, dx, sigmu, ts, tz);
-            pass_c<P2>(p2, c2, CE2, b2, dx, sigmu, ts, tz);
-            t = max_(ts, tz);
-            a = min_(1.0, 0.99 * (t > 1.0 ? 1.0 / t : 1.0)); /* pdip.py:462 */
+            if (probe_vec(dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
+            tm[0] = 0.0;
+            tm[1] = 0.0;
+            pass_c<P1>(p1, c1, CE1, b1, dx, sigmu, tm);
+            pass_c<P2>(p2, c2, CE2, b2, dx, sigmu, tm);
+            t = max_(tm[0], tm[1]);
+            a = min_(1.0, 0.99 * (t > 1.0 ? rcp_(t) : 1.0)); /* pdip.py:462 */
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) x[j] += a * dx[j];
             pass_d<P1>(c1, b1, a);

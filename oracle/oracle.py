@@ -13,26 +13,28 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcol_oracle.so")
+LIB_PATH_FMA = os.path.join(HERE, "libdcol_oracle_fma.so")   # same source, fused multiply-adds allowed
 
 GRAD_NONE, GRAD_FD, GRAD_EXACT = 0, 1, 2
 MAX_M, MAX_N, MAX_TRACE = 72, 8, 51
 
-_lib = None
+_libs = {}
 
 
 def build(force: bool = False) -> str:
-    """Compile the oracle with the committed Makefile (gcc only, a second or two)."""
+    """Compile the oracle (both roundings) with the committed Makefile (gcc only, a second or two)."""
     src = os.path.join(HERE, "dcol_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    stale = any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(src) for p in (LIB_PATH, LIB_PATH_FMA))
+    if force or stale:
         subprocess.run(["make", "-C", HERE, "-s"] + (["-B"] if force else []), check=True)
     return LIB_PATH
 
 
-def lib():
-    global _lib
+def lib(fma: bool = False):
+    _lib = _libs.get(fma)
     if _lib is None:
         build()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(LIB_PATH_FMA if fma else LIB_PATH)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L.dcol_oracle_pair.restype = C.c_int
         L.dcol_oracle_pair.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, dp, dp, C.c_double, C.c_int,
@@ -44,7 +46,7 @@ def lib():
         L.dcol_oracle_assemble.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip]
         L.dcol_oracle_dcm.restype = None
         L.dcol_oracle_dcm.argtypes = [dp, dp, dp]
-        _lib = L
+        _lib = _libs[fma] = L
     return _lib
 
 
@@ -83,8 +85,9 @@ def solve_pair(records, A, b, i1, i2, pose1, pose2, tol=1e-6, grad_mode=GRAD_FD)
 
 
 def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, grad_mode=GRAD_FD, threads=None,
-                want_contact=True):
-    """Batch -> dict(alpha[B], contact[B,3], grad[B,12], iters[B], status[B])."""
+                want_contact=True, fma=False):
+    """Batch -> dict(alpha[B], contact[B,3], grad[B,12], iters[B], status[B]).
+    ``fma=True`` runs the fused-multiply-add build (rounding-sensitivity probe, see Makefile)."""
     records, A, b = _table(records, A, b)
     idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
     idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
@@ -97,7 +100,7 @@ def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, grad_mode=GRA
     iters = np.empty(B, dtype=np.int32)
     status = np.empty(B, dtype=np.int32)
     null = C.POINTER(C.c_double)()
-    lib().dcol_oracle_batch(records.ctypes.data, _dp(A), _dp(b), _ip(idx1), _ip(idx2), _dp(pose1), _dp(pose2), B,
+    lib(fma).dcol_oracle_batch(records.ctypes.data, _dp(A), _dp(b), _ip(idx1), _ip(idx2), _dp(pose1), _dp(pose2), B,
                             float(tol), int(grad_mode), int(threads or os.cpu_count() or 1), _dp(alpha),
                             _dp(contact) if contact is not None else null, _dp(grad) if grad is not None else null,
                             _ip(iters), _ip(status))
