@@ -209,6 +209,7 @@ cudaError_t launch_group(const dcol_shape_table* T, int32_t i1, int32_t i2, cons
     case CLS_SPHERE: return launch_first_class<CLS_SPHERE>(c2, g, stream);
     case CLS_PGON5: return launch_first_class<CLS_PGON5>(c2, g, stream);
     case CLS_PGONN: return launch_first_class<CLS_PGONN>(c2, g, stream);
+    case CLS_BOX: return launch_first_class<CLS_BOX>(c2, g, stream);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -263,7 +264,9 @@ int dcol_shape_table_create(const dcol_shape* shapes, int32_t n_shapes, const do
     T->cls.resize(n_shapes);
     for (int i = 0; i < n_shapes; ++i) {
         const dcol_shape& s = T->shapes[i];
-        const int c = shape_class(s);
+        const bool faces_ok = !(s.type == DCOL_POLYTOPE || s.type == DCOL_POLYGON) ||
+                              (s.face_off >= 0 && s.n_faces >= 0 && s.face_off + s.n_faces <= n_faces);
+        const int c = faces_ok ? shape_class(s, T->A.data()) : -1;
         const bool faces = s.type == DCOL_POLYTOPE || s.type == DCOL_POLYGON;
         if (c < 0 || (faces && (s.face_off < 0 || s.face_off + s.n_faces > n_faces))) {
             delete T;

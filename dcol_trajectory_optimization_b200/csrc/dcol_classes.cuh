@@ -4,7 +4,7 @@
  * The reference dispatches on isinstance for every pair it evaluates
  * (primitives/problem_matrices.py:255-364).  Here a shape is classified ONCE, when the shape table
  * is created: its class fixes the primitive kind and, for the face counts that occur in the
- * reference's scenes (6-face boxes from create_rect_prism, the 8-face polytope of
+ * reference's scenes (axis-aligned boxes from create_rect_prism, other 6-face polytopes, the 8-face polytope of
  * systems/polytopes.jld2, the 5-gon of create_n_sided(5, .)), the number of half-spaces, so that a
  * pair of classes selects one fully unrolled, register-resident kernel.  Other face counts
  * (1..DCOL_MAX_FACES) fall to the runtime-count specialisations of the same code.
@@ -17,7 +17,7 @@
 namespace dcol {
 
 enum {
-    CLS_POLY6 = 0, CLS_POLY8, CLS_POLYN, CLS_CAPSULE, CLS_CYLINDER, CLS_CONE, CLS_SPHERE, CLS_PGON5, CLS_PGONN,
+    CLS_POLY6 = 0, CLS_POLY8, CLS_POLYN, CLS_CAPSULE, CLS_CYLINDER, CLS_CONE, CLS_SPHERE, CLS_PGON5, CLS_PGONN, CLS_BOX,
     N_CLS
 };
 
@@ -31,13 +31,25 @@ template <> struct ClassPrim<CLS_CONE> { typedef Prim<DCOL_CONE, 0> type; };
 template <> struct ClassPrim<CLS_SPHERE> { typedef Prim<DCOL_SPHERE, 0> type; };
 template <> struct ClassPrim<CLS_PGON5> { typedef Prim<DCOL_POLYGON, 5> type; };
 template <> struct ClassPrim<CLS_PGONN> { typedef Prim<DCOL_POLYGON, 0> type; };
+template <> struct ClassPrim<CLS_BOX> { typedef Prim<KIND_BOX, 6> type; };
 
-/* class of a shape record, or -1 if the record is malformed */
-inline int shape_class(const dcol_shape& s)
+/* faces exactly [I; -I] (create_rect_prism, misc_primitive_constructor.py:103-110) */
+inline bool is_axis_box(const dcol_shape& s, const double* A)
+{
+    if (s.type != DCOL_POLYTOPE || s.n_faces != 6 || !A) return false;
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 3; ++j)
+            if (A[3 * (s.face_off + i) + j] != ((j == i % 3) ? (i < 3 ? 1.0 : -1.0) : 0.0)) return false;
+    return true;
+}
+
+/* class of a shape record (A: the packed faces), or -1 if the record is malformed */
+inline int shape_class(const dcol_shape& s, const double* A)
 {
     switch (s.type) {
     case DCOL_POLYTOPE:
         if (s.n_faces < 1 || s.n_faces > DCOL_MAX_FACES) return -1;
+        if (is_axis_box(s, A)) return CLS_BOX;
         return s.n_faces == 6 ? CLS_POLY6 : (s.n_faces == 8 ? CLS_POLY8 : CLS_POLYN);
     case DCOL_POLYGON:
         if (s.n_faces < 1 || s.n_faces > DCOL_MAX_FACES) return -1;
@@ -110,6 +122,7 @@ inline bool dispatch_class2(int c2, F& f)
         DCOL_CASE2(CLS_SPHERE)
         DCOL_CASE2(CLS_PGON5)
         DCOL_CASE2(CLS_PGONN)
+        DCOL_CASE2(CLS_BOX)
     default: return false;
     }
 #undef DCOL_CASE2
@@ -128,6 +141,7 @@ inline bool dispatch_classes(int c1, int c2, F& f)
     case CLS_SPHERE: return dispatch_class2<CLS_SPHERE>(c2, f);
     case CLS_PGON5: return dispatch_class2<CLS_PGON5>(c2, f);
     case CLS_PGONN: return dispatch_class2<CLS_PGONN>(c2, f);
+    case CLS_BOX: return dispatch_class2<CLS_BOX>(c2, f);
     default: return false;
     }
 }

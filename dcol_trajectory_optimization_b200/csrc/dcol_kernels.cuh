@@ -147,6 +147,7 @@ template <> cudaError_t launch_first_class<CLS_CONE>(int, const GroupLaunch&, cu
 template <> cudaError_t launch_first_class<CLS_SPHERE>(int, const GroupLaunch&, cudaStream_t);
 template <> cudaError_t launch_first_class<CLS_PGON5>(int, const GroupLaunch&, cudaStream_t);
 template <> cudaError_t launch_first_class<CLS_PGONN>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_BOX>(int, const GroupLaunch&, cudaStream_t);
 
 #define DCOL_DEFINE_FIRST_CLASS(C1)                                                              \
     namespace dcol {                                                                             \

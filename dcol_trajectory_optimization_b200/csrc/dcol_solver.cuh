@@ -161,6 +161,7 @@ struct ShapeConst {
 /* y = Q'^T (x - r') and e its own extra decision variables.  In these variables every row of  */
 /* the primitive's block of G x - h has constant coefficients:                                 */
 /*   polytope  face i   :  A_i . y - b_i alpha                 problem_matrices.py:181-209     */
+/*   box       face i   :  +-y_(i mod 3) - b_i alpha           (polytope with A = [I; -I])     */
 /*   cone      orthant  :  y0 - (H/4) alpha                    problem_matrices.py:125-148     */
 /*             soc(3)   :  (-tanb y0 - (3/4) H tanb alpha, -y1, -y2)                           */
 /*   capsule   orthant  :  -(L/2) alpha +- e0                  problem_matrices.py:4-44        */
@@ -170,15 +171,20 @@ struct ShapeConst {
 /*   polygon   face i   :  -b_i alpha + A_i0 e0 + A_i1 e1      problem_matrices.py:90-120      */
 /*             soc(4)   :  (-R alpha, -y0 + e0, -y1 + e1, -y2)                                 */
 
+/* Internal kind: a polytope whose faces are exactly A = [I; -I] (create_rect_prism,
+ * misc_primitive_constructor.py:91-142 — every box of the reference's scenes).  Same rows as the
+ * polytope, but each has two non-zeros (+-y_k, -b_i alpha), known at compile time. */
+constexpr int KIND_BOX = 100;
+
 template <int KIND, int FC>
 struct Prim {
     static constexpr int kind = KIND;
-    static constexpr bool has_faces = (KIND == DCOL_POLYTOPE || KIND == DCOL_POLYGON);
+    static constexpr bool has_faces = (KIND == DCOL_POLYTOPE || KIND == DCOL_POLYGON || KIND == KIND_BOX);
     static constexpr bool dyn = has_faces && FC == 0;                       /* runtime face count      */
     static constexpr int FMAX = has_faces ? (FC ? FC : DCOL_MAX_FACES) : 0; /* sized for               */
     static constexpr int NO = has_faces ? FMAX : (KIND == DCOL_CONE ? 1 : KIND == DCOL_CAPSULE ? 2 : KIND == DCOL_CYLINDER ? 4 : 0);
     static constexpr int NOA = NO > 0 ? NO : 1;                             /* array extent            */
-    static constexpr int Q = KIND == DCOL_POLYTOPE ? 0 : (KIND == DCOL_CONE ? 3 : 4);
+    static constexpr int Q = (KIND == DCOL_POLYTOPE || KIND == KIND_BOX) ? 0 : (KIND == DCOL_CONE ? 3 : 4);
     static constexpr int QA = Q > 0 ? Q : 1;
     static constexpr int NE = (KIND == DCOL_CAPSULE || KIND == DCOL_CYLINDER) ? 1 : (KIND == DCOL_POLYGON ? 2 : 0);
     static constexpr int NL = 4 + NE;
@@ -197,6 +203,7 @@ struct Prim {
     {
         switch (KIND) {
         case DCOL_POLYTOPE: return j < 4;
+        case KIND_BOX: return j == 3 || j == i % 3;
         case DCOL_POLYGON: return j >= 3;
         case DCOL_CONE: return j == 0 || j == 3;
         case DCOL_CAPSULE: return j == 3 || j == 4;
@@ -209,6 +216,7 @@ struct Prim {
     {
         switch (KIND) {
         case DCOL_POLYTOPE: return j < 3 ? c.A[i][j] : -c.b[i];
+        case KIND_BOX: return j == 3 ? -c.b[i] : (i < 3 ? 1.0 : -1.0);
         case DCOL_POLYGON: return j == 3 ? -c.b[i] : c.A[i][j - 4];
         case DCOL_CONE: return j == 0 ? 1.0 : -0.25 * c.H;
         case DCOL_CAPSULE: return j == 3 ? -0.5 * c.L : (i == 0 ? 1.0 : -1.0);
@@ -683,24 +691,17 @@ struct Solver {
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) rzq[i] = B.sq[i] + rq[i];
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, rzq, B.ieta, B.tq); /* rho~ = W^-1 rz */
-            /* explicit W^-1 and W^-2 = W^-T W^-1 for the Gram block */
-            double Wi[P::QA][P::QA], W2[P::QA][P::QA];
-            Wi[0][0] = B.ieta * B.wh[0];
-            DCOL_UNROLL
-            for (int i = 1; i < P::Q; ++i) {
-                Wi[0][i] = Wi[i][0] = B.ieta * B.wh[i];
+            /* W^-2 for the Gram block.  Wbar(w)^2 = 2 w w^T - J for w^T J w = 1, so
+             * W^-2 = (2 wh wh^T - J) / eta^2: ten products instead of forming W^-1 and squaring it. */
+            double W2[P::QA][P::QA];
+            {
+                const double ie2 = B.ieta * B.ieta, t2 = 2.0 * ie2;
                 DCOL_UNROLL
-                for (int j = i; j < P::Q; ++j)
-                    Wi[i][j] = Wi[j][i] = B.ieta * ((i == j ? 1.0 : 0.0) + B.bw * (B.wh[i] * B.wh[j]));
-            }
-            DCOL_UNROLL
-            for (int i = 0; i < P::Q; ++i) {
-                DCOL_UNROLL
-                for (int j = i; j < P::Q; ++j) {
-                    double t = 0.0;
+                for (int i = 0; i < P::Q; ++i) {
+                    const double ti = t2 * B.wh[i];
                     DCOL_UNROLL
-                    for (int r = 0; r < P::Q; ++r) t += Wi[r][i] * Wi[r][j];
-                    W2[i][j] = t;
+                    for (int j = i; j < P::Q; ++j)
+                        W2[i][j] = (i == j) ? fma(ti, B.wh[j], i == 0 ? -ie2 : ie2) : ti * B.wh[j];
                 }
             }
             P::soc_gram(c, W2, Gl);

@@ -58,7 +58,7 @@ struct RunOne {
 void run_pair(const PairIn& in, PairOut& out, bool trace)
 {
     for (int i = 0; i <= DCOL_MAX_ITER; ++i) out.mu[i] = NAN;
-    int c1 = shape_class(*in.s1), c2 = shape_class(*in.s2);
+    int c1 = shape_class(*in.s1, in.A), c2 = shape_class(*in.s2, in.A);
     RunOne f = { &in, &out, trace };
     if (c1 < 0 || c2 < 0 || !dispatch_classes(c1, c2, f)) {
         out.status = DCOL_STATUS_UNSUPPORTED;
