@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=1 << 23, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=1, help="chunks per step when N > 1 (gather/solve overlap)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 21, help="pairs per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -186,14 +187,19 @@ def main():
     eng = d.ProximityEngine((rec, A, b), device=local_rank)
     fp64_peak = d.measure_fp64_peak(local_rank)
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
-    plan = eng.plan(i1, i2)
-    flat, out = parallel.alloc_packed(B, dev)
-    gathered = torch.empty((world, flat.numel()), dtype=torch.float64, device=dev) if world > 1 else None
+    # the rank's batch in chunks: chunk c's records are gathered (side stream) while chunk c+1 is solved
+    n_chunks = args.chunks if world > 1 else 1
+    bounds = [parallel.shard_bounds(B, c, n_chunks) for c in range(n_chunks)]
+    plans = [eng.plan(i1[lo:hi], i2[lo:hi]) for lo, hi in bounds]
+    pipe = parallel.GatherPipeline(bounds, world, dev, with_contact=True)
+    n_launches = sum(p.n_launches for p in plans)
+
+    def launch(c, out):
+        lo, hi = bounds[c]
+        eng.solve(plans[c], d1[lo:hi], d2[lo:hi], out=out)
 
     def step():
-        eng.solve(plan, d1, d2, out=out)
-        if world > 1:
-            parallel.all_gather_packed(flat, B, world, out=gathered)
+        pipe.step(launch)
 
     def barrier():
         if world > 1:
@@ -214,10 +220,8 @@ def main():
     ev[0].record()
     for s in range(args.steps):
         kev[s][0].record()
-        eng.solve(plan, d1, d2, out=out)
+        step()
         kev[s][1].record()
-        if world > 1:
-            parallel.all_gather_packed(flat, B, world, out=gathered)
     ev[1].record()
     barrier()
     t1 = time.time()
@@ -229,8 +233,9 @@ def main():
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = B * world / (ms_per_step * 1e-3)
 
-    iters = out.iters.cpu().numpy()
-    n_fail = int((out.status != 0).sum())
+    mine = pipe.rank_results(rank)          # N > 1: read this rank's records back out of the gathered buffers
+    iters = torch.cat([r.iters for r in mine]).cpu().numpy()
+    n_fail = int(sum(int((r.status != 0).sum()) for r in mine))
     flops = flop_model_total(rec, i1, i2, iters)
     kernel_ms = float(kms)
     achieved = flops / (kernel_ms * 1e-3)
@@ -273,17 +278,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "type_pairs": plan.n_groups,
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "type_pairs": plans[0].n_groups,
                        "mean_pdip_iters": float(iters.mean()), "failed_pairs": n_fail,
                        "l2": "inputs larger than L2 (805 MB of poses per step at the default size)",
-                       "collective": "one all_gather_into_tensor of 136 B/pair records per step" if world > 1 else "none",
+                       "collective": (f"all_gather_into_tensor of the 112 B/pair records (alpha, grad[12], iters, status), "
+                                      f"{n_chunks} chunks per step, chunk c gathered while chunk c+1 is solved") if world > 1 else "none",
                        "parallelism": f"batch sharded over {world} GPU(s), one process per GPU"},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": args.steps * plan.n_launches,
+            "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "dcol::pair_kernel<P1,P2> (40 specialisations, one launch each per step)",
+                         "kernel": f"dcol::pair_kernel<P1,P2> ({plans[0].n_groups} specialisations, {n_launches} launches per step)",
                          "kernel_ms_per_step": kernel_ms, "model_flops_per_pair": flops / B,
                          "peak_source": "dcol_measure_fp64_peak in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm": {"achieved": bytes_alg / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

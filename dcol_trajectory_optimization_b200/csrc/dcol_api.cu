@@ -68,6 +68,12 @@ struct dcol_shape_table {
     std::vector<dcol_shape> shapes;
     std::vector<int> cls;
     std::vector<double> A, b;
+    /* group launches of one solve fan out over side streams (fork/join on the caller's stream), so the
+     * tail of one group's grid overlaps the head of the next and small groups run concurrently */
+    static constexpr int kSide = 8;
+    std::mutex launch_mu;
+    cudaStream_t side[kSide] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[kSide] = {};
     /* host entry point state */
     std::mutex mu;
     HostScratch scratch[2];
@@ -292,6 +298,11 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
     }
     for (int i = 0; i < 4; ++i)
         if (T->streams[i]) cudaStreamDestroy(T->streams[i]);
+    for (int i = 0; i < dcol_shape_table::kSide; ++i) {
+        if (T->side[i]) cudaStreamDestroy(T->side[i]);
+        if (T->join_ev[i]) cudaEventDestroy(T->join_ev[i]);
+    }
+    if (T->fork_ev) cudaEventDestroy(T->fork_ev);
     delete T;
 }
 
@@ -401,20 +412,46 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
         ((flags & DCOL_WANT_GRAD) && !d_grad))
         return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null buffer");
     cudaStream_t stream = (cudaStream_t)stream_;
-    DCOL_CUDA(cudaSetDevice(P->table->device));
+    dcol_shape_table* T = const_cast<dcol_shape_table*>(P->table);
+    DCOL_CUDA(cudaSetDevice(T->device));
     (void)cudaGetLastError(); /* drop a stale error left by another library in this process */
-    for (const Group& g : P->groups) {
+    const int n_groups = (int)P->groups.size();
+    const int n_side = n_groups > 1 ? std::min(n_groups, (int)dcol_shape_table::kSide) : 0;
+    std::lock_guard<std::mutex> lock(T->launch_mu);
+    if (n_side) {
+        if (!T->fork_ev) DCOL_CUDA(cudaEventCreateWithFlags(&T->fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < n_side; ++i) {
+            if (!T->side[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->side[i], cudaStreamNonBlocking));
+            if (!T->join_ev[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->join_ev[i], cudaEventDisableTiming));
+        }
+        DCOL_CUDA(cudaEventRecord(T->fork_ev, stream));
+        for (int i = 0; i < n_side; ++i) DCOL_CUDA(cudaStreamWaitEvent(T->side[i], T->fork_ev, 0));
+    }
+    /* largest groups first: the long grids start early, the short ones fill the tail */
+    std::vector<int> order(n_groups);
+    for (int i = 0; i < n_groups; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P->groups[a].count > P->groups[b].count; });
+    int rc = 0;
+    for (int oi = 0; oi < n_groups && rc == 0; ++oi) {
+        const Group& g = P->groups[order[oi]];
+        cudaStream_t st = n_side ? T->side[oi % n_side] : stream;
         BatchArgs a = { P->d_perm, g.first, g.count, d_pose1, d_pose2, tol, max_iter, flags,
                         d_alpha, d_contact, d_grad, d_iters, d_status, nullptr };
+        cudaError_t e;
         if (!g.supported) {
-            fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, stream>>>(a);
-            DCOL_CUDA(cudaGetLastError());
-            continue;
+            fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, st>>>(a);
+            e = cudaGetLastError();
+        } else {
+            e = launch_group(T, g.i1, g.i2, a, st);
         }
-        cudaError_t e = launch_group(P->table, g.i1, g.i2, a, stream);
-        if (e != cudaSuccess) return fail_cuda(e, "pair_kernel launch");
+        if (e != cudaSuccess) rc = fail_cuda(e, "pair_kernel launch");
     }
-    return 0;
+    for (int i = 0; i < n_side; ++i) { /* join even after a failed launch: nothing may outlive the call's stream order */
+        cudaError_t e = cudaEventRecord(T->join_ev[i], T->side[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, T->join_ev[i], 0);
+        if (e != cudaSuccess && rc == 0) rc = fail_cuda(e, "stream join");
+    }
+    return rc;
 }
 
 /* Host buffers: the batch is cut into chunks that flow through three streams (copy in, plan + solve,

@@ -4,9 +4,12 @@ returned with ONE all-gather (BASELINE.json north_star).
 Every (candidate x knot x obstacle) pair is an independent solve, so there is no exchange during
 the solve.  The solve writes its outputs straight into one flat buffer per rank,
 
-    [ alpha (B) | grad (12 B) | contact (3 B) | iters, status (B int32 pairs) ]   float64 words
+    [ alpha (B) | grad (12 B) | iters, status (B int32 each) ]   14 float64 words = 112 bytes per pair
 
-so the gather is a single ``all_gather_into_tensor`` over NVLink with no packing pass.
+so the gather is a single ``all_gather_into_tensor`` over NVLink with no packing pass (the contact
+point, which no caller of the reference consumes across ranks, stays on the rank that computed it).
+:class:`GatherPipeline` cuts a rank's batch into chunks and gathers chunk *c* on a side stream while
+chunk *c+1* is being solved, so that only the last chunk's transfer is exposed.
 Works with any ``torch.distributed`` backend (NCCL on GPUs; gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -15,7 +18,7 @@ import torch
 
 from .engine import BatchResult
 
-WORDS_PER_PAIR = 1 + 12 + 3 + 1   # float64 words of one pair's record (136 bytes)
+WORDS_PER_PAIR = 1 + 12 + 1   # float64 words of one pair's record (112 bytes)
 
 
 def shard_bounds(n_items: int, rank: int, world: int) -> tuple[int, int]:
@@ -33,14 +36,17 @@ def packed_views(flat: torch.Tensor, B: int) -> BatchResult:
         raise ValueError("flat must be a contiguous float64 tensor of WORDS_PER_PAIR * B words")
     alpha = flat[:B]
     grad = flat[B:13 * B].view(B, 12)
-    contact = flat[13 * B:16 * B].view(B, 3)
-    ints = flat[16 * B:17 * B].view(torch.int32)          # 2 B int32 words
-    return BatchResult(alpha=alpha, contact=contact, grad=grad, iters=ints[:B], status=ints[B:])
+    ints = flat[13 * B:14 * B].view(torch.int32)          # 2 B int32 words
+    return BatchResult(alpha=alpha, contact=None, grad=grad, iters=ints[:B], status=ints[B:])
 
 
-def alloc_packed(B: int, device) -> tuple[torch.Tensor, BatchResult]:
+def alloc_packed(B: int, device, with_contact: bool = False) -> tuple[torch.Tensor, BatchResult]:
+    """One rank's record buffer and its views; ``with_contact`` adds a rank-local ``[B, 3]`` contact buffer."""
     flat = torch.empty(WORDS_PER_PAIR * B, dtype=torch.float64, device=device)
-    return flat, packed_views(flat, B)
+    views = packed_views(flat, B)
+    if with_contact:
+        views.contact = torch.empty((B, 3), dtype=torch.float64, device=device)
+    return flat, views
 
 
 def all_gather_packed(flat: torch.Tensor, B: int, world: int, out: torch.Tensor | None = None, group=None,
@@ -73,7 +79,7 @@ def sharded_solve(solve_local, n_pairs: int, rank: int, world: int, device, grou
     flat.zero_()
     lo, hi = bounds[rank]
     n = hi - lo
-    local = BatchResult(alpha=views.alpha[:n], contact=views.contact[:n], grad=views.grad[:n],
+    local = BatchResult(alpha=views.alpha[:n], contact=None, grad=views.grad[:n],
                         iters=views.iters[:n], status=views.status[:n])
     solve_local(lo, hi, local)
     if world == 1:
@@ -83,6 +89,45 @@ def sharded_solve(solve_local, n_pairs: int, rank: int, world: int, device, grou
     for r, (rlo, rhi) in enumerate(bounds):
         v = packed_views(gathered[r], Bmax)
         k = rhi - rlo
-        outs.append((rlo, rhi, BatchResult(alpha=v.alpha[:k], contact=v.contact[:k], grad=v.grad[:k],
+        outs.append((rlo, rhi, BatchResult(alpha=v.alpha[:k], contact=None, grad=v.grad[:k],
                                            iters=v.iters[:k], status=v.status[:k])))
     return outs
+
+
+class GatherPipeline:
+    """Chunked solve with the all-gather of chunk c overlapped with the solve of chunk c+1.
+
+    ``bounds``: the chunk boundaries of this rank's batch (equal on all ranks).  ``launch(c, out)`` must
+    enqueue the solve of chunk ``c`` on the current stream, writing ``out`` (views of the chunk's record
+    buffer).  ``step()`` enqueues one whole pass; it returns with the main stream waiting on the last
+    gather, so the caller's event/synchronize brackets see the complete step."""
+
+    def __init__(self, bounds, world: int, device, with_contact: bool = True, group=None):
+        self.bounds, self.world, self.group = list(bounds), world, group
+        self.flat, self.out, self.gathered = [], [], []
+        for lo, hi in self.bounds:
+            f, v = alloc_packed(hi - lo, device, with_contact=with_contact)
+            self.flat.append(f)
+            self.out.append(v)
+            self.gathered.append(torch.empty((world, f.numel()), dtype=torch.float64, device=device)
+                                 if world > 1 else None)
+        self.comm = torch.cuda.Stream(device=device) if world > 1 else None
+        self.events = [torch.cuda.Event() for _ in self.bounds] if world > 1 else []
+
+    def step(self, launch):
+        main = torch.cuda.current_stream()
+        for c, (lo, hi) in enumerate(self.bounds):
+            launch(c, self.out[c])
+            if self.world > 1:
+                self.events[c].record(main)
+                self.comm.wait_event(self.events[c])
+                with torch.cuda.stream(self.comm):
+                    all_gather_packed(self.flat[c], hi - lo, self.world, out=self.gathered[c], group=self.group)
+        if self.world > 1:
+            main.wait_stream(self.comm)
+
+    def rank_results(self, rank: int) -> list[BatchResult]:
+        """Per-chunk views of ``rank``'s records after a step (the local buffers if ``world == 1``)."""
+        if self.world == 1:
+            return self.out
+        return [packed_views(g[rank], hi - lo) for g, (lo, hi) in zip(self.gathered, self.bounds)]

@@ -26,7 +26,6 @@ def _worker(rank, world, port, n_pairs, ret):
         r = O.solve_batch(rec, A, b, i1[lo:hi], i2[lo:hi], p1[lo:hi], p2[lo:hi], grad_mode=O.GRAD_EXACT, threads=2)
         out.alpha.copy_(torch.from_numpy(r["alpha"]))
         out.grad.copy_(torch.from_numpy(r["grad"]))
-        out.contact.copy_(torch.from_numpy(r["contact"]))
         out.iters.copy_(torch.from_numpy(r["iters"]))
         out.status.copy_(torch.from_numpy(r["status"]))
 
@@ -61,9 +60,10 @@ def test_shard_bounds_and_packed_views():
         assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
     flat, v = parallel.alloc_packed(5, "cpu")
     assert flat.numel() == 5 * parallel.WORDS_PER_PAIR
-    v.alpha.fill_(1.0); v.grad.fill_(2.0); v.contact.fill_(3.0); v.iters.fill_(4); v.status.fill_(5)
+    assert parallel.WORDS_PER_PAIR * 8 == 112 and v.contact is None
+    v.alpha.fill_(1.0); v.grad.fill_(2.0); v.iters.fill_(4); v.status.fill_(5)
     w = parallel.packed_views(flat.clone(), 5)
-    assert float(w.alpha.sum()) == 5 and float(w.grad.sum()) == 120 and float(w.contact.sum()) == 45
+    assert float(w.alpha.sum()) == 5 and float(w.grad.sum()) == 120
     assert w.iters.tolist() == [4] * 5 and w.status.tolist() == [5] * 5
     with pytest.raises(ValueError):
         parallel.packed_views(flat[:-1], 5)
