@@ -158,7 +158,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=1 << 23, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunks", type=int, default=1, help="chunks per step when N > 1 (gather/solve overlap)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how records reach all ranks")
+    ap.add_argument("--chunks", type=int, default=1, help="--gather nccl: chunks per step (gather/solve overlap)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 21, help="pairs per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -187,19 +188,43 @@ def main():
     eng = d.ProximityEngine((rec, A, b), device=local_rank)
     fp64_peak = d.measure_fp64_peak(local_rank)
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
-    # the rank's batch in chunks: chunk c's records are gathered (side stream) while chunk c+1 is solved
-    n_chunks = args.chunks if world > 1 else 1
+    # N > 1, default: the all-gather is FUSED into the solve — the kernel's epilogue stores every 112-byte record
+    # into slot `rank` of every rank's gathered buffer (local + NVLink peer mappings); a 4-byte all-reduce on
+    # the same stream is the completion handshake.  --gather nccl: solve, then all_gather_into_tensor.
+    mode = "none" if world == 1 else args.gather
+    peer = None
+    if mode == "fused":
+        try:
+            peer = parallel.PeerRecordGather(B, rank, world, local_rank)
+        except Exception as exc:            # no CUDA IPC between the ranks on this box
+            if rank == 0:
+                print(f"# fused gather unavailable ({exc}); using NCCL all-gather", file=sys.stderr, flush=True)
+            mode = "nccl"
+        flag = torch.tensor([1.0 if mode == "fused" else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) == 0.0:
+            mode = "nccl"
+    n_chunks = args.chunks if mode == "nccl" else 1
     bounds = [parallel.shard_bounds(B, c, n_chunks) for c in range(n_chunks)]
     plans = [eng.plan(i1[lo:hi], i2[lo:hi]) for lo, hi in bounds]
-    pipe = parallel.GatherPipeline(bounds, world, dev, with_contact=True)
     n_launches = sum(p.n_launches for p in plans)
+    pipe = None
+    if mode == "fused":
+        contact = torch.empty((B, 3), dtype=torch.float64, device=dev)
+        plan_perm = plans[0].perm()
 
-    def launch(c, out):
-        lo, hi = bounds[c]
-        eng.solve(plans[c], d1[lo:hi], d2[lo:hi], out=out)
+        def step():
+            eng.solve_records(plans[0], d1, d2, peer.dest_ptrs, contact=contact)
+            peer.handshake()
+    else:
+        pipe = parallel.GatherPipeline(bounds, world if mode == "nccl" else 1, dev, with_contact=True)
 
-    def step():
-        pipe.step(launch)
+        def launch(c, out):
+            lo, hi = bounds[c]
+            eng.solve(plans[c], d1[lo:hi], d2[lo:hi], out=out)
+
+        def step():
+            pipe.step(launch)
 
     def barrier():
         if world > 1:
@@ -233,7 +258,14 @@ def main():
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = B * world / (ms_per_step * 1e-3)
 
-    mine = pipe.rank_results(rank)          # N > 1: read this rank's records back out of the gathered buffers
+    if mode == "fused":                     # read this rank's records back out of a PEER's view of them: slot `rank`
+        from dcol_trajectory_optimization_b200.engine import records_to_result
+        chk = torch.zeros(1, dtype=torch.float64, device=dev)
+        mine = [records_to_result(peer.gathered[rank], plan_perm)]
+        for r in range(world):              # every slot of my gathered buffer was filled by rank r's kernel
+            chk += (records_to_result(peer.gathered[r]).status != 0).sum()
+    else:
+        mine = pipe.rank_results(rank)      # nccl: this rank's records out of the gathered buffers
     iters = torch.cat([r.iters for r in mine]).cpu().numpy()
     n_fail = int(sum(int((r.status != 0).sum()) for r in mine))
     flops = flop_model_total(rec, i1, i2, iters)
@@ -281,8 +313,11 @@ def main():
             "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "type_pairs": plans[0].n_groups,
                        "mean_pdip_iters": float(iters.mean()), "failed_pairs": n_fail,
                        "l2": "inputs larger than L2 (805 MB of poses per step at the default size)",
-                       "collective": (f"all_gather_into_tensor of the 112 B/pair records (alpha, grad[12], iters, status), "
-                                      f"{n_chunks} chunks per step, chunk c gathered while chunk c+1 is solved") if world > 1 else "none",
+                       "collective": {"none": "none",
+                                      "fused": "all-gather fused into the solve: the kernel epilogue stores each 112 B record "
+                                               "(alpha, grad[12], iters, status) to every rank's buffer over NVLink peer "
+                                               "mappings; 4-byte NCCL all-reduce as completion handshake",
+                                      "nccl": f"all_gather_into_tensor of the 112 B/pair records, {n_chunks} chunk(s) per step"}[mode],
                        "parallelism": f"batch sharded over {world} GPU(s), one process per GPU"},
             "clocks": clocks,
             "e2e": e2e,

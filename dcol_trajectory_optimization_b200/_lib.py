@@ -17,12 +17,15 @@ CSRC = os.path.join(HERE, "csrc")
 WANT_CONTACT, WANT_GRAD = 1, 2
 MAX_ITER = 50
 MAX_M, MAX_N = 72, 8
+MAX_DEST, RECORD_WORDS = 8, 14
 
 #: every symbol include/dcol.h declares (checked by the CPU test-suite against the built library)
 SYMBOLS = (
     "dcol_version", "dcol_last_error", "dcol_device_count", "dcol_shape_table_create", "dcol_shape_table_destroy",
     "dcol_plan_create", "dcol_plan_destroy", "dcol_plan_size", "dcol_plan_n_groups", "dcol_plan_n_launches",
     "dcol_proximity_batch_device", "dcol_proximity_batch_host", "dcol_host_alloc", "dcol_host_free",
+    "dcol_proximity_batch_records", "dcol_plan_perm", "dcol_device_alloc", "dcol_device_free", "dcol_ipc_export",
+    "dcol_ipc_import", "dcol_ipc_close",
     "dcol_debug_trace_pair", "dcol_measure_fp64_peak",
 )
 
@@ -77,6 +80,21 @@ def lib():
     L.dcol_proximity_batch_host.restype = C.c_int
     L.dcol_proximity_batch_host.argtypes = [vp, ip, ip, dp, dp, C.c_int64, C.c_double, C.c_int32, C.c_uint32,
                                             dp, dp, dp, ip, ip]
+    L.dcol_proximity_batch_records.restype = C.c_int
+    L.dcol_proximity_batch_records.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+                                               C.c_int64, dp, vp]
+    L.dcol_plan_perm.restype = C.c_void_p
+    L.dcol_plan_perm.argtypes = [vp]
+    L.dcol_device_alloc.restype = C.c_int
+    L.dcol_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.dcol_device_free.restype = None
+    L.dcol_device_free.argtypes = [C.c_int, vp]
+    L.dcol_ipc_export.restype = C.c_int
+    L.dcol_ipc_export.argtypes = [C.c_int, vp, vp]
+    L.dcol_ipc_import.restype = C.c_int
+    L.dcol_ipc_import.argtypes = [C.c_int, vp, C.POINTER(C.c_void_p)]
+    L.dcol_ipc_close.restype = None
+    L.dcol_ipc_close.argtypes = [C.c_int, vp]
     L.dcol_host_alloc.restype = C.c_int
     L.dcol_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.dcol_host_free.restype = None

@@ -5,6 +5,7 @@
  * compute entry point fails with DCOL_E_NOGPU.
  */
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -176,11 +177,19 @@ __global__ void fill_unsupported(BatchArgs b)
     if (t >= b.count) return;
     const int64_t k = b.perm ? (int64_t)b.perm[b.first + t] : b.first + t;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (b.flags & DCOL_WANT_CONTACT)
+        for (int j = 0; j < 3; ++j) b.contact[3 * k + j] = nan;
+    if (b.n_dest > 0) {
+        for (int d = 0; d < b.n_dest; ++d) {
+            double* r = b.dest[d] + kRecordWords * (b.record_offset + b.first + t);
+            for (int j = 0; j < 13; ++j) r[j] = nan;
+            r[13] = __longlong_as_double((long long)DCOL_STATUS_UNSUPPORTED << 32);
+        }
+        return;
+    }
     b.status[k] = DCOL_STATUS_UNSUPPORTED;
     b.iters[k] = 0;
     b.alpha[k] = nan;
-    if (b.flags & DCOL_WANT_CONTACT)
-        for (int j = 0; j < 3; ++j) b.contact[3 * k + j] = nan;
     if (b.flags & DCOL_WANT_GRAD)
         for (int j = 0; j < 12; ++j) b.grad[12 * k + j] = nan;
 }
@@ -400,6 +409,10 @@ int64_t dcol_plan_size(const dcol_plan* P) { return P ? P->B : 0; }
 int32_t dcol_plan_n_groups(const dcol_plan* P) { return P ? (int32_t)P->groups.size() : 0; }
 int32_t dcol_plan_n_launches(const dcol_plan* P) { return P ? P->n_launches : 0; }
 
+static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol, int32_t max_iter,
+                      uint32_t flags, double* d_alpha, double* d_contact, double* d_grad, int32_t* d_iters,
+                      int32_t* d_status, int32_t n_dest, double* const* dest, int64_t record_offset, void* stream_);
+
 int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
                                 int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact, double* d_grad,
                                 int32_t* d_iters, int32_t* d_status, void* stream_)
@@ -411,6 +424,31 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
     if (!d_pose1 || !d_pose2 || !d_alpha || !d_iters || !d_status || ((flags & DCOL_WANT_CONTACT) && !d_contact) ||
         ((flags & DCOL_WANT_GRAD) && !d_grad))
         return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null buffer");
+    return solve_plan(P, d_pose1, d_pose2, tol, max_iter, flags, d_alpha, d_contact, d_grad, d_iters, d_status, 0, nullptr, 0,
+                      stream_);
+}
+
+int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
+                                 int32_t max_iter, int32_t n_dest, double* const* dest, int64_t record_offset,
+                                 double* d_contact, void* stream_)
+{
+    if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_records: null plan");
+    if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
+    if (n_dest < 1 || n_dest > DCOL_MAX_DEST || !dest || record_offset < 0) return fail(DCOL_E_ARG, "bad destination list");
+    for (int d = 0; d < n_dest; ++d)
+        if (!dest[d] || ((uintptr_t)dest[d] & 15)) return fail(DCOL_E_ARG, "record destinations must be 16-byte aligned");
+    if (P->B == 0) return 0;
+    if (!d_pose1 || !d_pose2) return fail(DCOL_E_ARG, "dcol_proximity_batch_records: null buffer");
+    return solve_plan(P, d_pose1, d_pose2, tol, max_iter, d_contact ? DCOL_WANT_CONTACT : 0u, nullptr, d_contact, nullptr,
+                      nullptr, nullptr, n_dest, dest, record_offset, stream_);
+}
+
+const int32_t* dcol_plan_perm(const dcol_plan* P) { return P ? P->d_perm : nullptr; }
+
+static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol, int32_t max_iter,
+                      uint32_t flags, double* d_alpha, double* d_contact, double* d_grad, int32_t* d_iters,
+                      int32_t* d_status, int32_t n_dest, double* const* dest, int64_t record_offset, void* stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
     dcol_shape_table* T = const_cast<dcol_shape_table*>(P->table);
     DCOL_CUDA(cudaSetDevice(T->device));
@@ -436,7 +474,8 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
         const Group& g = P->groups[order[oi]];
         cudaStream_t st = n_side ? T->side[oi % n_side] : stream;
         BatchArgs a = { P->d_perm, g.first, g.count, d_pose1, d_pose2, tol, max_iter, flags,
-                        d_alpha, d_contact, d_grad, d_iters, d_status, nullptr };
+                        d_alpha, d_contact, d_grad, d_iters, d_status, nullptr, n_dest, record_offset, {} };
+        for (int d = 0; d < n_dest; ++d) a.dest[d] = dest[d];
         cudaError_t e;
         if (!g.supported) {
             fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, st>>>(a);
@@ -550,6 +589,50 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
     return rc;
 }
 
+/* Device buffers that other processes of the node can map (CUDA IPC): the record buffers of the fused
+ * all-gather.  Plain cudaMalloc allocations, so the IPC handle refers to exactly this buffer. */
+int dcol_device_alloc(int device, size_t bytes, void** out)
+{
+    if (!out) return fail(DCOL_E_ARG, "null argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DCOL_CUDA(cudaSetDevice(device));
+    DCOL_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+    return 0;
+}
+void dcol_device_free(int device, void* p)
+{
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+int dcol_ipc_export(int device, void* dev_ptr, void* handle64)
+{
+    if (!dev_ptr || !handle64) return fail(DCOL_E_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DCOL_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    DCOL_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+/* Maps a peer process's buffer into this process (enables peer access between the two GPUs). */
+int dcol_ipc_import(int device, const void* handle64, void** out)
+{
+    if (!handle64 || !out) return fail(DCOL_E_ARG, "null argument");
+    DCOL_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    DCOL_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+void dcol_ipc_close(int device, void* p)
+{
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaIpcCloseMemHandle(p);
+}
+
 /* page-locked host memory, so that the host entry point's copies run asynchronously at PCIe rate */
 int dcol_host_alloc(size_t bytes, void** out)
 {
@@ -593,7 +676,7 @@ int dcol_debug_trace_pair(const dcol_shape_table* T, int32_t idx1, int32_t idx2,
     cudaError_t e = cudaMemcpy(d, h, sizeof(Dev), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         BatchArgs a = { nullptr, 0, 1, d->pose, d->pose + 6, tol, DCOL_MAX_ITER, 0u,
-                        &d->alpha, nullptr, nullptr, &d->iters, &d->status, &d->tr };
+                        &d->alpha, nullptr, nullptr, &d->iters, &d->status, &d->tr, 0, 0, {} };
         e = launch_group(T, idx1, idx2, a, 0);
     }
     if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(Dev), cudaMemcpyDeviceToHost);

@@ -21,6 +21,9 @@ namespace dcol {
 #ifndef DCOL_THREADS
 #define DCOL_THREADS 64
 #endif
+#ifndef DCOL_MAX_DEST
+#define DCOL_MAX_DEST 8 /* destinations of a record-mode solve: the local buffer + up to 7 NVLink peers */
+#endif
 #ifndef DCOL_MIN_BLOCKS
 #define DCOL_MIN_BLOCKS 4
 #endif
@@ -42,6 +45,12 @@ struct BatchArgs {
     int32_t* iters;  /* [B]      */
     int32_t* status; /* [B]      */
     struct TraceOut* trace; /* debug entry point only (count == 1): mu trace and world-frame (x, s, z) */
+    /* record mode (n_dest > 0): instead of the separate arrays, every pair's 112-byte record
+     * {alpha, grad[12], iters | status << 32} goes, in PLAN order, to dest[d] + 14 * (record_offset + first + t)
+     * for each destination d; destinations may be peer-GPU memory (the all-gather is fused into the solve) */
+    int32_t n_dest;
+    int64_t record_offset;
+    double* dest[DCOL_MAX_DEST];
 };
 
 /* one pair with the mu trace and the world-frame (x, s, z): the debug entry point */
@@ -57,11 +66,16 @@ struct GroupArgs {
     BatchArgs b;
 };
 
+constexpr int kRecordWords = 14;
+constexpr int kStageBytes = (kThreads / 32) * 32 * kRecordWords * 8;
+
 template <class P1, class P2>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
 {
     typedef Solver<P1, P2> S;
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    /* lanes of this warp that own a pair (a prefix of the warp); taken while all 32 lanes are still here */
+    const unsigned lanes = __ballot_sync(0xffffffffu, t < a.b.count);
     if (t >= a.b.count) return;
     const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + t] : a.b.first + t;
 
@@ -73,7 +87,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid
     }
     S sv;
     PairResult<S::N> res;
-    const bool want_grad = (a.b.flags & DCOL_WANT_GRAD) != 0;
+#ifdef DCOL_NO_RECORDS
+    const bool records = false;
+#else
+    const bool records = a.b.n_dest > 0;
+#endif
+    const bool want_grad = records || (a.b.flags & DCOL_WANT_GRAD) != 0;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     Trace tr = { nullptr };
     if (a.b.trace) {
@@ -81,23 +100,49 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid
         for (int i = 0; i <= DCOL_MAX_ITER; ++i) tr.mu[i] = nan;
     }
     const int st = sv.solve(a.c1, a.c2, pose1, pose2, a.b.tol, a.b.max_iter, want_grad, res, &tr);
-    a.b.status[k] = st;
-    a.b.iters[k] = res.iters;
-    a.b.alpha[k] = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
+    const double alpha = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
     if (a.b.flags & DCOL_WANT_CONTACT) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = st == DCOL_STATUS_OK ? sv.x[j] : nan; /* proximity.py:52 */
     }
+    double g[12];
     if (want_grad) {
-        double g[12];
         if (st == DCOL_STATUS_OK) {
             sv.gradient(a.c1, a.c2, pose1, pose2, g);
         } else {
 #pragma unroll
             for (int j = 0; j < 12; ++j) g[j] = nan;
         }
+    }
+    if (!records) {
+        a.b.status[k] = st;
+        a.b.iters[k] = res.iters;
+        a.b.alpha[k] = alpha;
+        if (want_grad) {
 #pragma unroll
-        for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+            for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+        }
+    } else {
+        /* Record mode.  A warp's records are contiguous in plan order: transpose them through shared memory
+         * and write them with 16-byte stores that cover whole 128-byte lines, once per destination (local
+         * memory or a peer GPU's over NVLink). */
+        extern __shared__ __align__(16) double stage_all[]; /* kStageBytes, passed only by record-mode launches */
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        double* stage_w = stage_all + w * (32 * kRecordWords);
+        double* mine = stage_w + lane * kRecordWords;
+        mine[0] = alpha;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) mine[1 + j] = g[j];
+        mine[13] = __longlong_as_double((long long)(uint32_t)res.iters | ((long long)st << 32));
+        __syncwarp(lanes);
+        const int n_lanes = __popc(lanes);
+        const int n_chunks = n_lanes * (kRecordWords / 2);
+        const double2* src = reinterpret_cast<const double2*>(stage_w);
+        const int64_t t0 = t - lane; /* first pair of this warp */
+        for (int d = 0; d < a.b.n_dest; ++d) {
+            double2* dst = reinterpret_cast<double2*>(a.b.dest[d] + kRecordWords * (a.b.record_offset + a.b.first + t0));
+            for (int c = lane; c < n_chunks; c += n_lanes) dst[c] = src[c];
+        }
     }
     if (a.b.trace) {
         TraceOut* out = a.b.trace;
@@ -131,7 +176,7 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
     a.b = g.args;
     if (g.args.count <= 0) return cudaSuccess;
     const int64_t blocks = (g.args.count + kThreads - 1) / kThreads;
-    pair_kernel<P1, P2><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
+    pair_kernel<P1, P2><<<(unsigned)blocks, kThreads, g.args.n_dest > 0 ? kStageBytes : 0, stream>>>(a);
     return cudaGetLastError();
 }
 

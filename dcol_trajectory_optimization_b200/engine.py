@@ -53,6 +53,36 @@ class BatchResult:
     status: object     # [B]      DCOL_STATUS_*
 
 
+class _DevArray:
+    """A raw device address exposed through ``__cuda_array_interface__`` so torch can view it."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def device_view(ptr: int, shape, device, typestr="<f8"):
+    """Torch view (no copy) of a raw device allocation, e.g. one made by ``dcol_device_alloc``."""
+    import torch
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+def records_to_result(rec, perm=None) -> BatchResult:
+    """Views of a ``[B, 14]`` float64 record tensor (plan order); with ``perm`` the fields are scattered back
+    to pair order (copies)."""
+    import torch
+    alpha, grad = rec[:, 0], rec[:, 1:13]
+    ints = rec[:, 13].contiguous().view(torch.int32).view(-1, 2)
+    iters, status = ints[:, 0], ints[:, 1]
+    if perm is None:
+        return BatchResult(alpha=alpha, contact=None, grad=grad, iters=iters, status=status)
+    p = perm.long()
+    out = BatchResult(alpha=torch.empty_like(alpha), contact=None, grad=torch.empty_like(grad),
+                      iters=torch.empty_like(iters), status=torch.empty_like(status))
+    out.alpha[p], out.grad[p], out.iters[p], out.status[p] = alpha, grad, iters, status
+    return out
+
+
 class Plan:
     """A batch's pairs grouped by shape pair (device counting sort), reusable across solves."""
 
@@ -71,6 +101,14 @@ class Plan:
         self._handle = handle
         self.n_groups = int(_lib.lib().dcol_plan_n_groups(handle))
         self.n_launches = int(_lib.lib().dcol_plan_n_launches(handle))
+
+    def perm(self):
+        """int32 CUDA tensor ``[size]``: ``perm[i]`` = index of the i-th pair in plan order (a copy)."""
+        import torch
+        ptr = _lib.lib().dcol_plan_perm(self._handle)
+        if not ptr or self.size == 0:
+            return torch.zeros(0, dtype=torch.int32, device=self.engine.device)
+        return torch.as_tensor(_DevArray(ptr, (self.size,), "<i4"), device=self.engine.device).clone()
 
     def close(self):
         if getattr(self, "_handle", None):
@@ -149,6 +187,22 @@ class ProximityEngine:
             out.contact.data_ptr() if out.contact is not None else None,
             out.grad.data_ptr() if out.grad is not None else None, out.iters.data_ptr(), out.status.data_ptr(), stream))
         return out
+
+    def solve_records(self, plan: Plan, pose1, pose2, dest_ptrs, record_offset: int = 0, tol: float = 1e-6,
+                      max_iter: int = 50, contact=None):
+        """Record mode: every pair's 112-byte record ``{alpha, grad[12], iters, status}`` is written, in plan
+        order, to each of the raw device addresses ``dest_ptrs`` (local buffers or peer-GPU buffers mapped with
+        CUDA IPC — the all-gather of the results fused into the solve).  Enqueues on the current stream."""
+        import torch
+        B = plan.size
+        for name, t in (("pose1", pose1), ("pose2", pose2)):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (B, 6)):
+                raise ValueError(f"{name} must be a contiguous float64 CUDA tensor of shape ({B}, 6)")
+        arr = (C.c_void_p * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().dcol_proximity_batch_records(
+            plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter), len(dest_ptrs), arr,
+            int(record_offset), contact.data_ptr() if contact is not None else None, stream))
 
     # ------------------------------------------------------------------ host buffers
     def solve_host(self, idx1, idx2, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,

@@ -131,3 +131,64 @@ class GatherPipeline:
         if self.world == 1:
             return self.out
         return [packed_views(g[rank], hi - lo) for g, (lo, hi) in zip(self.gathered, self.bounds)]
+
+
+class PeerRecordGather:
+    """The all-gather fused into the solve: every rank's kernel writes its 112-byte records straight into
+    slot ``rank`` of EVERY rank's gathered buffer, locally and over NVLink peer mappings (CUDA IPC), from
+    the kernel's epilogue.  Nothing is packed, copied or sent afterwards; a scalar all-reduce on the same
+    stream is the completion handshake (when it returns on a rank's stream, every peer's kernel — and with
+    it every peer's stores into this rank's buffer — has completed).
+
+    ``gathered``: this rank's ``[world, B, 14]`` float64 tensor (plan order per source rank; use
+    ``engine.records_to_result(gathered[r], perm_r)`` for pair order).  All ranks must use the same ``B``.
+    """
+
+    def __init__(self, B: int, rank: int, world: int, local_device: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        from .engine import device_view
+        if world > _lib.MAX_DEST:
+            raise ValueError(f"at most {_lib.MAX_DEST} ranks per node")
+        L = _lib.lib()
+        self.B, self.rank, self.world, self.dev, self.group = B, rank, world, local_device, group
+        nbytes = world * B * _lib.RECORD_WORDS * 8
+        ptr = C.c_void_p()
+        _lib.check(L.dcol_device_alloc(local_device, nbytes, C.byref(ptr)))
+        self._ptr = ptr.value
+        self.gathered = device_view(self._ptr, (world, max(B, 1), _lib.RECORD_WORDS), torch.device("cuda", local_device))
+        self.gathered = self.gathered[:, :B]
+        handle = (C.c_ubyte * 64)()
+        self._peers = {}
+        if world > 1:
+            _lib.check(L.dcol_ipc_export(local_device, self._ptr, C.cast(handle, C.c_void_p)))
+            mine = (local_device, bytes(handle))
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            for r, (_, h) in enumerate(everyone):
+                if r == rank:
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(L.dcol_ipc_import(local_device, C.cast(buf, C.c_void_p), C.byref(p)))
+                self._peers[r] = p.value
+        slot = B * _lib.RECORD_WORDS * 8 * rank      # this rank's slot inside every destination buffer
+        self.dest_ptrs = [(self._ptr if r == rank else self._peers[r]) + slot for r in range(world)]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=torch.device("cuda", local_device))
+
+    def handshake(self):
+        """Stream-ordered completion barrier (4-byte all-reduce)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        from . import _lib
+        L = _lib.lib()
+        for p in self._peers.values():
+            L.dcol_ipc_close(self.dev, p)
+        self._peers = {}
+        if self._ptr:
+            L.dcol_device_free(self.dev, self._ptr)
+            self._ptr = None

@@ -125,6 +125,30 @@ int dcol_proximity_batch_device(const dcol_plan* plan, const double* d_pose1, co
                                 int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact,
                                 double* d_grad, int32_t* d_iters, int32_t* d_status, void* stream);
 
+/* Record mode, for multi-GPU use: every pair's results go out as ONE 112-byte record
+ *     { double alpha; double grad[12]; int32 iters; int32 status; }
+ * written in PLAN order (record i belongs to pair dcol_plan_perm()[i]) at dest[d] + 14 * (record_offset + i)
+ * doubles, for each of the n_dest (1..DCOL_MAX_DEST) destinations.  A destination may be memory of a peer
+ * GPU mapped with dcol_ipc_import: the kernel's epilogue then stores the records over NVLink, i.e. the
+ * all-gather of the results (BASELINE.json north_star) is fused into the solve.  Destinations must be
+ * 16-byte aligned.  d_contact ([B][3], pair order) is optional.  dest is a HOST array of device pointers. */
+#define DCOL_MAX_DEST 8
+#define DCOL_RECORD_WORDS 14
+int dcol_proximity_batch_records(const dcol_plan* plan, const double* d_pose1, const double* d_pose2, double tol,
+                                 int32_t max_iter, int32_t n_dest, double* const* dest, int64_t record_offset,
+                                 double* d_contact, void* stream);
+/* Device pointer to the plan's permutation: perm[i] = index (in the caller's arrays) of the i-th pair in
+ * plan order; valid until dcol_plan_destroy. */
+const int32_t* dcol_plan_perm(const dcol_plan* plan);
+
+/* Device buffers other processes of the node can map through CUDA IPC (64-byte handles), used for the
+ * record buffers of the fused all-gather: rank r allocates, exports, every other rank imports. */
+int  dcol_device_alloc(int device, size_t bytes, void** out);
+void dcol_device_free(int device, void* p);
+int  dcol_ipc_export(int device, void* dev_ptr, void* handle64);
+int  dcol_ipc_import(int device, const void* handle64, void** out);
+void dcol_ipc_close(int device, void* p);
+
 /* Same computation with HOST buffers: the batch flows in chunks through copy-in, plan + solve and
  * copy-out streams (device scratch cached in the table), then the call synchronises.  This is the
  * call a reference-side binding makes.  Calls on one table are serialised. */

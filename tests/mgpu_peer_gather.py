@@ -1,0 +1,53 @@
+"""Run under torchrun (one process per GPU): checks parallel.PeerRecordGather, the all-gather fused into
+the solve kernel's epilogue over CUDA-IPC peer mappings.  Used by tests/test_gpu_parity.py."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dcol_trajectory_optimization_b200 as d  # noqa: E402
+from dcol_trajectory_optimization_b200 import parallel, workloads as W  # noqa: E402
+from dcol_trajectory_optimization_b200.engine import records_to_result  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    B = 50_001
+    # every rank can rebuild every rank's inputs (seed = 100 + rank), so it can check all gathered slots
+    batches = [W.config4_batch(B, seed=100 + r) for r in range(world)]
+    shapes, i1, i2, p1, p2 = batches[rank]
+    eng = d.ProximityEngine(shapes, device=local)
+    plan = eng.plan(i1, i2)
+    d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
+    pg = parallel.PeerRecordGather(B, rank, world, local)
+    pg.gathered.fill_(-1.0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    eng.solve_records(plan, d1, d2, pg.dest_ptrs)
+    pg.handshake()
+    torch.cuda.synchronize()
+    # every rank's perm differs: exchange them once (static per plan)
+    perms = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(world)]
+    dist.all_gather(perms, plan.perm())
+    for r in range(world):
+        _, j1, j2, q1, q2 = batches[r]
+        pl = eng.plan(j1, j2)
+        want = eng.solve(pl, torch.from_numpy(q1).to(dev), torch.from_numpy(q2).to(dev))
+        got = records_to_result(pg.gathered[r], perms[r])
+        torch.cuda.synchronize()
+        assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status), f"rank {rank} slot {r}"
+        assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad), f"rank {rank} slot {r}"
+    print("PEER_GATHER_OK", rank, flush=True)
+    dist.barrier()
+    pg.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -245,3 +245,54 @@ def test_full_size_properties(dcol):
     assert float(((r.alpha[ss] - exact).abs() / exact).max()) < 3e-4   # mu < 1e-6 leaves alpha this far from alpha*
     plan.close()
     eng.close()
+
+
+def test_record_mode_matches_array_mode(dcol):
+    """Record mode (the fused all-gather's output format): 112-byte records in plan order, written to
+    several destinations, equal the separate arrays bit for bit; unsupported pairs carry status 4."""
+    import torch
+    from dcol_trajectory_optimization_b200 import workloads as W
+    from dcol_trajectory_optimization_b200.engine import records_to_result
+    shapes, i1, i2, p1, p2 = W.config4_batch(10_007, seed=5)
+    i2 = i2.copy()
+    i1 = i1.copy()
+    i1[:50], i2[:50] = 2, 3                                   # capsule x cylinder: the reference cannot assemble these
+    eng = dcol.ProximityEngine(shapes)
+    plan = eng.plan(i1, i2)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    ref = eng.solve(plan, d1, d2)
+    B, off = plan.size, 3
+    recs = [torch.full((B + 8, 14), -7.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    contact = torch.empty((B, 3), dtype=torch.float64, device="cuda")
+    eng.solve_records(plan, d1, d2, [r.data_ptr() for r in recs], record_offset=off, contact=contact)
+    torch.cuda.synchronize()
+    perm = plan.perm()
+    assert sorted(perm.tolist()) == list(range(B))
+    for r in recs:
+        assert float(r[:off].min()) == -7.0 and float(r[off + B:].max()) == -7.0      # nothing outside the window
+        got = records_to_result(r[off:off + B], perm)
+        assert torch.equal(got.status, ref.status) and torch.equal(got.iters, ref.iters)
+        assert torch.equal(got.alpha.isnan(), ref.alpha.isnan())
+        ok = ref.status == 0
+        assert torch.equal(got.alpha[ok], ref.alpha[ok]) and torch.equal(got.grad[ok], ref.grad[ok])
+    assert int((ref.status == 4).sum()) == 50 + int(((torch.from_numpy(i1) == 2) & (torch.from_numpy(i2) == 3))[50:].sum())
+    assert torch.equal(contact[ref.status == 0], ref.contact[ref.status == 0])
+    plan.close()
+    eng.close()
+
+
+def test_peer_record_gather_two_gpus():
+    """The fused all-gather on 2 GPUs (one process per GPU, CUDA IPC peer mappings): every rank ends up
+    with every rank's records.  Skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "mgpu_peer_gather.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("PEER_GATHER_OK") == 2
