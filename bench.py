@@ -36,10 +36,17 @@ UNIT = "pairs/s"
 WORKLOAD = "config4: synthetic batched proximity sweep, 40 ordered type pairs x random poses, alpha + contact + grad[12]"
 
 
-def make_batch(n_pairs, seed):
+WORKLOAD5 = "config5: scaled quadrotor hallway, sphere victim vs 1024 obstacles (11 shapes) x 100 knots x candidates, alpha + contact + grad[12]"
+
+
+def make_batch(n_pairs, seed, workload="config4"):
     from dcol_trajectory_optimization_b200 import workloads as W
     from dcol_trajectory_optimization_b200.shapes import flatten_shapes
-    shapes, i1, i2, p1, p2 = W.config4_batch(n_pairs, seed=seed)
+    if workload == "config5":       # whole trajectories: n_pairs is rounded down to a multiple of 1024 x 100
+        n_cand = max(1, n_pairs // (1024 * 100))
+        shapes, i1, i2, p1, p2 = W.config5_batch(n_obs=1024, n_knots=100, n_cand=n_cand, seed=seed)
+    else:
+        shapes, i1, i2, p1, p2 = W.config4_batch(n_pairs, seed=seed)
     return flatten_shapes(shapes), i1, i2, p1, p2
 
 
@@ -161,6 +168,8 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how records reach all ranks")
     ap.add_argument("--chunks", type=int, default=1, help="--gather nccl: chunks per step (gather/solve overlap)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 21, help="pairs per step of the reference arm")
+    ap.add_argument("--workload", default="config4", choices=["config4", "config5"])
+    ap.add_argument("--no-altro", action="store_true", help="skip the three ALTRO scenario solves (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -184,7 +193,8 @@ def main():
     W = max(args.warmup, 3)
     B = args.pairs
 
-    (rec, A, b), i1, i2, p1, p2 = make_batch(B, 1234 + rank)
+    (rec, A, b), i1, i2, p1, p2 = make_batch(B, 1234 + rank, args.workload)
+    B = len(i1)
     eng = d.ProximityEngine((rec, A, b), device=local_rank)
     fp64_peak = d.measure_fp64_peak(local_rank)
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
@@ -310,7 +320,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "type_pairs": plans[0].n_groups,
+            "config": {"workload": WORKLOAD if args.workload == "config4" else WORKLOAD5, "pairs_per_gpu": B, "type_pairs": plans[0].n_groups,
                        "mean_pdip_iters": float(iters.mean()), "failed_pairs": n_fail,
                        "l2": "inputs larger than L2 (805 MB of poses per step at the default size)",
                        "collective": {"none": "none",
@@ -323,7 +333,10 @@ def main():
             "e2e": e2e,
             "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak,
+                         "traffic": {"dram_bytes_per_launch": 144.6e6, "pairs_per_launch": 209715,
+                                     "source": "profiles/r01_ncu_full_7kernels.md (ncu --set full, mean of 7 specialisations "
+                                               "at this size; algorithmic 236 B/pair = 49.5e6 B per launch)"},
                          "kernel": f"dcol::pair_kernel<P1,P2> ({plans[0].n_groups} specialisations, {n_launches} launches per step)",
                          "kernel_ms_per_step": kernel_ms, "model_flops_per_pair": flops / B,
                          "peak_source": "dcol_measure_fp64_peak in this run (MEASURED_PEAKS.json has no FP64 entry)",
@@ -331,6 +344,12 @@ def main():
                                  "frac": bytes_alg / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "bytes_per_pair": 236}},
         }
+        if world == 1 and not args.no_altro:
+            # BASELINE.json metric, second half: "ALTRO solve time" of the reference's three scenarios through the
+            # batched caller (altro/solver.py), every collision constraint on this GPU
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from run_altro import run as run_altro
+            line["altro"] = run_altro()
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
