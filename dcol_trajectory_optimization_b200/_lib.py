@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DCOL_LIB") or os.path.join(HERE, "libdcol_b200.so")   # DCOL_LIB: build experiments
 CSRC = os.path.join(HERE, "csrc")
 
-WANT_CONTACT, WANT_GRAD = 1, 2
+WANT_CONTACT, WANT_GRAD, FIX_CASE4 = 1, 2, 4
 MAX_ITER = 50
 MAX_M, MAX_N = 72, 8
 MAX_DEST, RECORD_WORDS = 8, 14
@@ -81,7 +81,7 @@ def lib():
     L.dcol_proximity_batch_host.argtypes = [vp, ip, ip, dp, dp, C.c_int64, C.c_double, C.c_int32, C.c_uint32,
                                             dp, dp, dp, ip, ip]
     L.dcol_proximity_batch_records.restype = C.c_int
-    L.dcol_proximity_batch_records.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+    L.dcol_proximity_batch_records.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p),
                                                C.c_int64, dp, vp]
     L.dcol_plan_perm.restype = C.c_void_p
     L.dcol_plan_perm.argtypes = [vp]

@@ -40,6 +40,27 @@ int fail_cuda(cudaError_t e, const char* where)
         if (e_ != cudaSuccess) return fail_cuda(e_, #call);    \
     } while (0)
 
+/* Makes `device` current for the scope of an API call and restores the caller's device afterwards
+ * (a host framework such as PyTorch must not find its current device changed). */
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err != cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define DCOL_DEVICE(device)                                                   \
+    DeviceGuard guard_(device);                                               \
+    if (guard_.err != cudaSuccess) return fail_cuda(guard_.err, "cudaSetDevice")
+
 struct Group {
     int32_t i1, i2;
     int64_t first, count;
@@ -225,6 +246,7 @@ cudaError_t launch_group(const dcol_shape_table* T, int32_t i1, int32_t i2, cons
     case CLS_PGON5: return launch_first_class<CLS_PGON5>(c2, g, stream);
     case CLS_PGONN: return launch_first_class<CLS_PGONN>(c2, g, stream);
     case CLS_BOX: return launch_first_class<CLS_BOX>(c2, g, stream);
+    case CLS_ELLIPSOID: return launch_first_class<CLS_ELLIPSOID>(c2, g, stream);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -296,7 +318,7 @@ int dcol_shape_table_create(const dcol_shape* shapes, int32_t n_shapes, const do
 void dcol_shape_table_destroy(dcol_shape_table* T)
 {
     if (!T) return;
-    cudaSetDevice(T->device);
+    DeviceGuard guard_(T->device);
     for (int i = 0; i < 2; ++i) {
         T->scratch[i].release();
         dcol_plan_destroy(T->plans[i]);
@@ -384,7 +406,7 @@ int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int
 {
     if (!T || !out || B < 0 || (B > 0 && (!d_idx1 || !d_idx2))) return fail(DCOL_E_ARG, "dcol_plan_create: bad argument");
     if (B > 0x7fffffffLL) return fail(DCOL_E_ARG, "dcol_plan_create: at most 2^31-1 pairs per plan");
-    DCOL_CUDA(cudaSetDevice(T->device));
+    DCOL_DEVICE(T->device);
     dcol_plan* P = nullptr;
     int rc = plan_alloc(T, B, &P);
     if (rc) return rc;
@@ -400,7 +422,7 @@ int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int
 void dcol_plan_destroy(dcol_plan* P)
 {
     if (!P) return;
-    cudaSetDevice(P->table->device);
+    DeviceGuard guard_(P->table->device);
     cudaFree(P->d_perm);
     cudaFree(P->d_counts);
     delete P;
@@ -419,7 +441,7 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
 {
     if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null plan");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
-    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4)) return fail(DCOL_E_ARG, "unknown flag");
     if (P->B == 0) return 0;
     if (!d_pose1 || !d_pose2 || !d_alpha || !d_iters || !d_status || ((flags & DCOL_WANT_CONTACT) && !d_contact) ||
         ((flags & DCOL_WANT_GRAD) && !d_grad))
@@ -429,9 +451,10 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
 }
 
 int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
-                                 int32_t max_iter, int32_t n_dest, double* const* dest, int64_t record_offset,
-                                 double* d_contact, void* stream_)
+                                 int32_t max_iter, uint32_t flags, int32_t n_dest, double* const* dest,
+                                 int64_t record_offset, double* d_contact, void* stream_)
 {
+    if (flags & ~(uint32_t)DCOL_FIX_CASE4) return fail(DCOL_E_ARG, "unknown flag");
     if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_records: null plan");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
     if (n_dest < 1 || n_dest > DCOL_MAX_DEST || !dest || record_offset < 0) return fail(DCOL_E_ARG, "bad destination list");
@@ -439,7 +462,7 @@ int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, cons
         if (!dest[d] || ((uintptr_t)dest[d] & 15)) return fail(DCOL_E_ARG, "record destinations must be 16-byte aligned");
     if (P->B == 0) return 0;
     if (!d_pose1 || !d_pose2) return fail(DCOL_E_ARG, "dcol_proximity_batch_records: null buffer");
-    return solve_plan(P, d_pose1, d_pose2, tol, max_iter, d_contact ? DCOL_WANT_CONTACT : 0u, nullptr, d_contact, nullptr,
+    return solve_plan(P, d_pose1, d_pose2, tol, max_iter, flags | (d_contact ? DCOL_WANT_CONTACT : 0u), nullptr, d_contact, nullptr,
                       nullptr, nullptr, n_dest, dest, record_offset, stream_);
 }
 
@@ -451,7 +474,7 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     dcol_shape_table* T = const_cast<dcol_shape_table*>(P->table);
-    DCOL_CUDA(cudaSetDevice(T->device));
+    DCOL_DEVICE(T->device);
     (void)cudaGetLastError(); /* drop a stale error left by another library in this process */
     const int n_groups = (int)P->groups.size();
     const int n_side = n_groups > 1 ? std::min(n_groups, (int)dcol_shape_table::kSide) : 0;
@@ -477,7 +500,7 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
                         d_alpha, d_contact, d_grad, d_iters, d_status, nullptr, n_dest, record_offset, {} };
         for (int d = 0; d < n_dest; ++d) a.dest[d] = dest[d];
         cudaError_t e;
-        if (!g.supported) {
+        if (!g.supported && !(flags & DCOL_FIX_CASE4)) {
             fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, st>>>(a);
             e = cudaGetLastError();
         } else {
@@ -502,13 +525,13 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
     dcol_shape_table* T = const_cast<dcol_shape_table*>(T_);
     if (!T || B < 0) return fail(DCOL_E_ARG, "dcol_proximity_batch_host: bad argument");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
-    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4)) return fail(DCOL_E_ARG, "unknown flag");
     if (B == 0) return 0;
     if (!idx1 || !idx2 || !pose1 || !pose2 || !alpha || !iters || !status || ((flags & DCOL_WANT_CONTACT) && !contact) ||
         ((flags & DCOL_WANT_GRAD) && !grad))
         return fail(DCOL_E_ARG, "dcol_proximity_batch_host: null buffer");
     std::lock_guard<std::mutex> lock(T->mu);
-    DCOL_CUDA(cudaSetDevice(T->device));
+    DCOL_DEVICE(T->device);
     for (int i = 0; i < 4; ++i)
         if (!T->streams[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -596,21 +619,21 @@ int dcol_device_alloc(int device, size_t bytes, void** out)
     if (!out) return fail(DCOL_E_ARG, "null argument");
     int rc = check_device(device);
     if (rc) return rc;
-    DCOL_CUDA(cudaSetDevice(device));
+    DCOL_DEVICE(device);
     DCOL_CUDA(cudaMalloc(out, bytes ? bytes : 16));
     return 0;
 }
 void dcol_device_free(int device, void* p)
 {
     if (!p) return;
-    cudaSetDevice(device);
+    DeviceGuard guard_(device);
     cudaFree(p);
 }
 int dcol_ipc_export(int device, void* dev_ptr, void* handle64)
 {
     if (!dev_ptr || !handle64) return fail(DCOL_E_ARG, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    DCOL_CUDA(cudaSetDevice(device));
+    DCOL_DEVICE(device);
     cudaIpcMemHandle_t h;
     DCOL_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
     memcpy(handle64, &h, 64);
@@ -620,7 +643,7 @@ int dcol_ipc_export(int device, void* dev_ptr, void* handle64)
 int dcol_ipc_import(int device, const void* handle64, void** out)
 {
     if (!handle64 || !out) return fail(DCOL_E_ARG, "null argument");
-    DCOL_CUDA(cudaSetDevice(device));
+    DCOL_DEVICE(device);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     DCOL_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
@@ -629,7 +652,7 @@ int dcol_ipc_import(int device, const void* handle64, void** out)
 void dcol_ipc_close(int device, void* p)
 {
     if (!p) return;
-    cudaSetDevice(device);
+    DeviceGuard guard_(device);
     cudaIpcCloseMemHandle(p);
 }
 
@@ -655,7 +678,7 @@ int dcol_debug_trace_pair(const dcol_shape_table* T, int32_t idx1, int32_t idx2,
         return fail(DCOL_E_ARG, "dcol_debug_trace_pair: null argument");
     const int32_t ns = (int32_t)T->shapes.size();
     if (idx1 < 0 || idx1 >= ns || idx2 < 0 || idx2 >= ns) return fail(DCOL_E_INDEX, "shape index out of range");
-    DCOL_CUDA(cudaSetDevice(T->device));
+    DCOL_DEVICE(T->device);
     const double nan = __builtin_nan("");
     *alpha = nan; *n = 0; *m = 0; *iters = 0;
     for (int i = 0; i <= DCOL_MAX_ITER; ++i) mu_trace[i] = nan;
@@ -699,7 +722,7 @@ int dcol_measure_fp64_peak(int device, double* flops_per_s)
     if (!flops_per_s) return fail(DCOL_E_ARG, "null argument");
     int rc = check_device(device);
     if (rc) return rc;
-    DCOL_CUDA(cudaSetDevice(device));
+    DCOL_DEVICE(device);
     cudaDeviceProp prop;
     DCOL_CUDA(cudaGetDeviceProperties(&prop, device));
     double* d = nullptr;

@@ -18,7 +18,7 @@ namespace dcol {
 
 enum {
     CLS_POLY6 = 0, CLS_POLY8, CLS_POLYN, CLS_CAPSULE, CLS_CYLINDER, CLS_CONE, CLS_SPHERE, CLS_PGON5, CLS_PGONN, CLS_BOX,
-    N_CLS
+    CLS_ELLIPSOID, N_CLS
 };
 
 template <int CLS> struct ClassPrim;
@@ -32,6 +32,7 @@ template <> struct ClassPrim<CLS_SPHERE> { typedef Prim<DCOL_SPHERE, 0> type; };
 template <> struct ClassPrim<CLS_PGON5> { typedef Prim<DCOL_POLYGON, 5> type; };
 template <> struct ClassPrim<CLS_PGONN> { typedef Prim<DCOL_POLYGON, 0> type; };
 template <> struct ClassPrim<CLS_BOX> { typedef Prim<KIND_BOX, 6> type; };
+template <> struct ClassPrim<CLS_ELLIPSOID> { typedef Prim<DCOL_ELLIPSOID, 0> type; };
 
 /* faces exactly [I; -I] (create_rect_prism, misc_primitive_constructor.py:103-110) */
 inline bool is_axis_box(const dcol_shape& s, const double* A)
@@ -58,6 +59,7 @@ inline int shape_class(const dcol_shape& s, const double* A)
     case DCOL_CYLINDER: return CLS_CYLINDER;
     case DCOL_CONE: return CLS_CONE;
     case DCOL_SPHERE: return CLS_SPHERE;
+    case DCOL_ELLIPSOID: return (s.R > 0.0 && s.L > 0.0 && s.H > 0.0) ? CLS_ELLIPSOID : -1;
     default: return -1;
     }
 }
@@ -70,9 +72,10 @@ inline bool class_has_extras(int cls)
  * carry extra decision variables (np.vstack raises ValueError) -> DCOL_STATUS_UNSUPPORTED */
 inline bool class_pair_supported(int c1, int c2) { return !(class_has_extras(c1) && class_has_extras(c2)); }
 
+/* every pair of classes has a kernel; whether a both-extras pair is SOLVED is a run-time flag (DCOL_FIX_CASE4) */
 template <int C1, int C2>
 struct PairSupported {
-    static constexpr bool value = !((ClassPrim<C1>::type::NE > 0) && (ClassPrim<C2>::type::NE > 0));
+    static constexpr bool value = true;
 };
 
 /* shape record + packed faces -> the uniform constant block of one specialisation */
@@ -83,6 +86,9 @@ inline void fill_const(const dcol_shape& s, const double* A, const double* b, Sh
     c.L = s.L;
     c.H = s.H;
     c.tanb = tan(s.beta);
+    c.ia[0] = s.R != 0.0 ? 1.0 / s.R : 0.0;
+    c.ia[1] = s.L != 0.0 ? 1.0 / s.L : 0.0;
+    c.ia[2] = s.H != 0.0 ? 1.0 / s.H : 0.0;
     for (int i = 0; i < 3; ++i) {
         c.r_off[i] = s.r_offset[i];
         for (int j = 0; j < 3; ++j) c.Q_off[i][j] = s.Q_offset[3 * i + j];
@@ -123,6 +129,7 @@ inline bool dispatch_class2(int c2, F& f)
         DCOL_CASE2(CLS_PGON5)
         DCOL_CASE2(CLS_PGONN)
         DCOL_CASE2(CLS_BOX)
+        DCOL_CASE2(CLS_ELLIPSOID)
     default: return false;
     }
 #undef DCOL_CASE2
@@ -142,6 +149,7 @@ inline bool dispatch_classes(int c1, int c2, F& f)
     case CLS_PGON5: return dispatch_class2<CLS_PGON5>(c2, f);
     case CLS_PGONN: return dispatch_class2<CLS_PGONN>(c2, f);
     case CLS_BOX: return dispatch_class2<CLS_BOX>(c2, f);
+    case CLS_ELLIPSOID: return dispatch_class2<CLS_ELLIPSOID>(c2, f);
     default: return false;
     }
 }

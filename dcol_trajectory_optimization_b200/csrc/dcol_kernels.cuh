@@ -193,6 +193,7 @@ template <> cudaError_t launch_first_class<CLS_SPHERE>(int, const GroupLaunch&, 
 template <> cudaError_t launch_first_class<CLS_PGON5>(int, const GroupLaunch&, cudaStream_t);
 template <> cudaError_t launch_first_class<CLS_PGONN>(int, const GroupLaunch&, cudaStream_t);
 template <> cudaError_t launch_first_class<CLS_BOX>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class<CLS_ELLIPSOID>(int, const GroupLaunch&, cudaStream_t);
 
 #define DCOL_DEFINE_FIRST_CLASS(C1)                                                              \
     namespace dcol {                                                                             \

@@ -149,6 +149,7 @@ DCOL_HD void dcm_derivative_contract(const double p[3], const double Q[3][3], co
 template <int FMAX>
 struct ShapeConst {
     double R, L, H, tanb;   /* tanb = tan(beta)                       */
+    double ia[3];           /* ellipsoid: inverse semi-axes           */
     double r_off[3];        /* body-frame origin offset               */
     double Q_off[3][3];     /* body-frame rotation offset             */
     int32_t nf, pad;        /* faces actually present                 */
@@ -169,6 +170,7 @@ struct ShapeConst {
 /*   cylinder  capsule + :  -+ y0 - (L/2) alpha                problem_matrices.py:47-87       */
 /*   sphere    soc(4)   :  (-R alpha, -y)   (y in world axes)  problem_matrices.py:151-178     */
 /*   polygon   face i   :  -b_i alpha + A_i0 e0 + A_i1 e1      problem_matrices.py:90-120      */
+/*   ellipsoid soc(4)   :  (-alpha, -y0/a, -y1/b, -y2/c)       extension, Report.pdf eq. 27    */
 /*             soc(4)   :  (-R alpha, -y0 + e0, -y1 + e1, -y2)                                 */
 
 /* Internal kind: a polytope whose faces are exactly A = [I; -I] (create_rect_prism,
@@ -189,7 +191,7 @@ struct Prim {
     static constexpr int NE = (KIND == DCOL_CAPSULE || KIND == DCOL_CYLINDER) ? 1 : (KIND == DCOL_POLYGON ? 2 : 0);
     static constexpr int NL = 4 + NE;
     static constexpr bool rot = KIND != DCOL_SPHERE;  /* the sphere's rows are written in world axes */
-    static constexpr bool ball = Q == 4;              /* soc rows (-R alpha, -y + E e)               */
+    static constexpr bool ball = Q == 4 && KIND != DCOL_ELLIPSOID; /* soc rows (-R alpha, -y + E e), world-frame duals */
     typedef ShapeConst<FMAX> Const;
     typedef Prim P;
 
@@ -235,6 +237,7 @@ struct Prim {
     DCOL_HD static double soc_c(const Const& c, int j)
     {
         if (KIND == DCOL_CONE) return j == 0 ? -c.tanb : (j == 3 ? -0.75 * c.H * c.tanb : -1.0);
+        if (KIND == DCOL_ELLIPSOID) return j < 3 ? -c.ia[j] : -1.0;
         return j < 3 ? -1.0 : (j == 3 ? -c.R : 1.0);
     }
 

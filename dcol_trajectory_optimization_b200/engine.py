@@ -23,7 +23,7 @@ from . import _lib
 from .shapes import (STATUS_MAX_ITER, STATUS_NON_FINITE, STATUS_NOT_PD, STATUS_OK, STATUS_UNSUPPORTED, flatten_shapes,
                      pose_of)
 
-WANT_CONTACT, WANT_GRAD = _lib.WANT_CONTACT, _lib.WANT_GRAD
+WANT_CONTACT, WANT_GRAD, FIX_CASE4 = _lib.WANT_CONTACT, _lib.WANT_GRAD, _lib.FIX_CASE4
 
 
 def raise_for_status(status: int):
@@ -162,7 +162,7 @@ class ProximityEngine:
         return Plan(self, torch.as_tensor(idx1), torch.as_tensor(idx2))
 
     def solve(self, plan: Plan, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
-              want_contact: bool = True, out: BatchResult | None = None) -> BatchResult:
+              want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False) -> BatchResult:
         """Enqueue the solve of every pair of ``plan`` on the current CUDA stream.
 
         ``pose1``/``pose2``: float64 CUDA tensors ``[B, 6]`` (rows ``r, p``).  Returns CUDA tensors;
@@ -180,7 +180,8 @@ class ProximityEngine:
                 grad=torch.empty((B, 12), dtype=torch.float64, device=dev) if want_grad else None,
                 iters=torch.empty(B, dtype=torch.int32, device=dev),
                 status=torch.empty(B, dtype=torch.int32, device=dev))
-        flags = (WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
+        flags = ((WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
+                 | (FIX_CASE4 if fix_case4 else 0))
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().dcol_proximity_batch_device(
             plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter), flags, out.alpha.data_ptr(),
@@ -189,7 +190,7 @@ class ProximityEngine:
         return out
 
     def solve_records(self, plan: Plan, pose1, pose2, dest_ptrs, record_offset: int = 0, tol: float = 1e-6,
-                      max_iter: int = 50, contact=None):
+                      max_iter: int = 50, contact=None, fix_case4: bool = False):
         """Record mode: every pair's 112-byte record ``{alpha, grad[12], iters, status}`` is written, in plan
         order, to each of the raw device addresses ``dest_ptrs`` (local buffers or peer-GPU buffers mapped with
         CUDA IPC — the all-gather of the results fused into the solve).  Enqueues on the current stream."""
@@ -201,12 +202,13 @@ class ProximityEngine:
         arr = (C.c_void_p * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().dcol_proximity_batch_records(
-            plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter), len(dest_ptrs), arr,
+            plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter),
+            FIX_CASE4 if fix_case4 else 0, len(dest_ptrs), arr,
             int(record_offset), contact.data_ptr() if contact is not None else None, stream))
 
     # ------------------------------------------------------------------ host buffers
     def solve_host(self, idx1, idx2, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
-                   want_contact: bool = True, out: BatchResult | None = None) -> BatchResult:
+                   want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False) -> BatchResult:
         """The reference-facing call: NumPy buffers in, NumPy buffers out, copies inside."""
         idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
         idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
@@ -219,7 +221,8 @@ class ProximityEngine:
             out = BatchResult(alpha=np.empty(B), contact=np.empty((B, 3)) if want_contact else None,
                               grad=np.empty((B, 12)) if want_grad else None, iters=np.empty(B, np.int32),
                               status=np.empty(B, np.int32))
-        flags = (WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
+        flags = ((WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
+                 | (FIX_CASE4 if fix_case4 else 0))
         _lib.check(_lib.lib().dcol_proximity_batch_host(
             self._table, idx1.ctypes.data, idx2.ctypes.data, pose1.ctypes.data, pose2.ctypes.data, B, float(tol),
             int(max_iter), flags, out.alpha.ctypes.data, out.contact.ctypes.data if out.contact is not None else None,

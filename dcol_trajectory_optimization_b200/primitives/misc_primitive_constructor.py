@@ -15,7 +15,7 @@ therefore reads them through ``numpy.asarray`` at call time.
 import numpy as np
 
 __all__ = [
-    "PolytopeMRP", "CapsuleMRP", "CylinderMRP", "ConeMRP", "SphereMRP", "PolygonMRP",
+    "PolytopeMRP", "CapsuleMRP", "CylinderMRP", "ConeMRP", "SphereMRP", "PolygonMRP", "EllipsoidMRP",
     "create_rect_prism", "create_n_sided",
 ]
 
@@ -40,6 +40,16 @@ class PolytopeMRP(_PrimitiveMRP):
         self.length = length
         self.width = width
         self.height = height
+
+
+class EllipsoidMRP(_PrimitiveMRP):
+    """EXTENSION (not in the reference's code; its report describes it, sec. 3.1.5): ellipsoid with semi-axes
+    ``(a, b, c)`` along the body axes, ``{y : |diag(1/a, 1/b, 1/c) y| <= alpha}``.  A general ellipsoid
+    ``y' P y <= 1`` is expressed by putting P's eigenvectors into ``Q_offset``."""
+
+    def __init__(self, a, b, c):
+        super().__init__()
+        self.semi_axes = (a, b, c)
 
 
 class CapsuleMRP(_PrimitiveMRP):

@@ -13,21 +13,21 @@ from __future__ import annotations
 import numpy as np
 
 # primitive kinds, in the order of SURVEY.md section 8 / include/dcol.h
-POLYTOPE, CAPSULE, CYLINDER, CONE, SPHERE, POLYGON = range(6)
-N_KINDS = 6
-KIND_NAMES = ("polytope", "capsule", "cylinder", "cone", "sphere", "polygon")
+POLYTOPE, CAPSULE, CYLINDER, CONE, SPHERE, POLYGON, ELLIPSOID = range(7)
+N_KINDS = 7      # ELLIPSOID is an extension: the reference's code has no such primitive (only its report does)
+KIND_NAMES = ("polytope", "capsule", "cylinder", "cone", "sphere", "polygon", "ellipsoid")
 
 #: extra decision variables a primitive adds beyond (x, alpha)
-KIND_EXTRAS = (0, 1, 1, 0, 0, 2)
+KIND_EXTRAS = (0, 1, 1, 0, 0, 2, 0)
 #: second-order-cone dimension of a primitive (0 = none)
-KIND_SOC = (0, 4, 4, 3, 4, 4)
+KIND_SOC = (0, 4, 4, 3, 4, 4, 4)
 
 #: most half-spaces one polytope / polygon may carry (device row arrays are sized for it)
 MAX_FACES = 32
 
 _CLASS_TO_KIND = {
     "PolytopeMRP": POLYTOPE, "CapsuleMRP": CAPSULE, "CylinderMRP": CYLINDER,
-    "ConeMRP": CONE, "SphereMRP": SPHERE, "PolygonMRP": POLYGON,
+    "ConeMRP": CONE, "SphereMRP": SPHERE, "PolygonMRP": POLYGON, "EllipsoidMRP": ELLIPSOID,
 }
 
 #: numpy mirror of ``struct dcol_shape`` (144 bytes, natural alignment)
@@ -53,7 +53,7 @@ def kind_of(prim) -> int:
 
 def n_ort_of(kind: int, n_faces: int) -> int:
     """Orthant rows a primitive contributes (problem_matrices.py:37-42,78-85,109,146,166,202)."""
-    return (n_faces, 2, 4, 1, 0, n_faces)[kind]
+    return (n_faces, 2, 4, 1, 0, n_faces, 0)[kind]
 
 
 def pair_supported(kind1: int, kind2: int) -> bool:
@@ -108,6 +108,10 @@ def flatten_shapes(prims):
         if kind == CONE:
             rec["H"] = float(prim.H)
             rec["beta"] = float(prim.beta)
+        if kind == ELLIPSOID:               # semi-axes along the body axes travel in (R, L, H)
+            rec["R"], rec["L"], rec["H"] = (float(v) for v in prim.semi_axes)
+            if min(rec["R"], rec["L"], rec["H"]) <= 0:
+                raise ValueError("ellipsoid semi-axes must be positive")
     A_packed = np.concatenate(A_rows) if A_rows else np.zeros((0, 3))
     b_packed = np.concatenate(b_rows) if b_rows else np.zeros((0,))
     return recs, np.ascontiguousarray(A_packed), np.ascontiguousarray(b_packed)

@@ -46,7 +46,9 @@ enum {
     DCOL_CONE     = 3, /* height H, half angle beta                problem_matrices.py:125-148 */
     DCOL_SPHERE   = 4, /* radius R                                 problem_matrices.py:151-178 */
     DCOL_POLYGON  = 5, /* planar {A y <= alpha b} padded by R      problem_matrices.py:90-120  */
-    DCOL_N_KINDS  = 6
+    DCOL_ELLIPSOID = 6, /* EXTENSION (absent from the reference's code, Report.pdf sec. 3.1.5 eq. 27):
+                           semi-axes (R, L, H) along the body axes; ||diag(1/R,1/L,1/H) Q'^T (x - r')|| <= alpha */
+    DCOL_N_KINDS  = 7
 };
 
 #define DCOL_MAX_FACES 32 /* most half-spaces of one polytope / polygon */
@@ -73,7 +75,12 @@ enum {
 /* output selection */
 enum {
     DCOL_WANT_CONTACT = 1u, /* x[0:3] of the solution, proximity.py:52                        */
-    DCOL_WANT_GRAD    = 2u  /* d alpha / d [r1 p1 r2 p2], proximity_gradient.py:71-77 layout  */
+    DCOL_WANT_GRAD    = 2u, /* d alpha / d [r1 p1 r2 p2], proximity_gradient.py:71-77 layout  */
+    DCOL_FIX_CASE4    = 4u  /* EXTENSION: also solve the pairs in which both primitives carry extra variables
+                               (capsule / cylinder / polygon squared), with the column layout
+                               [x, alpha, extras1, extras2] that combine_problem_matrices.py:58-67 builds for the
+                               second primitive but forgets to pad the first to; without this flag those pairs
+                               report DCOL_STATUS_UNSUPPORTED, as the reference raises ValueError */
 };
 
 /* One primitive SHAPE (no pose).  144 bytes, natural alignment. */
@@ -135,8 +142,8 @@ int dcol_proximity_batch_device(const dcol_plan* plan, const double* d_pose1, co
 #define DCOL_MAX_DEST 8
 #define DCOL_RECORD_WORDS 14
 int dcol_proximity_batch_records(const dcol_plan* plan, const double* d_pose1, const double* d_pose2, double tol,
-                                 int32_t max_iter, int32_t n_dest, double* const* dest, int64_t record_offset,
-                                 double* d_contact, void* stream);
+                                 int32_t max_iter, uint32_t flags /* DCOL_FIX_CASE4 or 0 */, int32_t n_dest,
+                                 double* const* dest, int64_t record_offset, double* d_contact, void* stream);
 /* Device pointer to the plan's permutation: perm[i] = index (in the caller's arrays) of the i-th pair in
  * plan order; valid until dcol_plan_destroy. */
 const int32_t* dcol_plan_perm(const dcol_plan* plan);

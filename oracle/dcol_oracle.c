@@ -131,6 +131,17 @@ static void blocks_from_adjusted(const dcol_shape* sh, const double* A, const do
         }
         break;
     }
+    case DCOL_ELLIPSOID: { /* EXTENSION, not in the reference's code (Report.pdf sec. 3.1.5 eq. 27): parity unpinned.
+                            * || U Q'^T (x - r') || <= alpha with U = diag(1/R, 1/L, 1/H) */
+        const double ia[3] = { 1.0 / sh->R, 1.0 / sh->L, 1.0 / sh->H };
+        out->n_ort = 0; out->n_soc = 4; out->v = 4;
+        out->G_soc[0][3] = -1.0;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) out->G_soc[1 + i][j] = -(ia[i] * Q[j][i]);
+            out->h_soc[1 + i] = out->G_soc[1 + i][0] * r[0] + out->G_soc[1 + i][1] * r[1] + out->G_soc[1 + i][2] * r[2];
+        }
+        break;
+    }
     case DCOL_POLYGON: { /* problem_matrices.py:90-120 */
         int f = sh->n_faces;
         out->n_ort = f; out->n_soc = 4; out->v = 6;
@@ -166,11 +177,37 @@ static void problem_matrices(const dcol_shape* sh, const double* A, const double
     blocks_from_adjusted(sh, A, b, rp, Qp, out);
 }
 
+/* EXTENSION switch (tests of DCOL_FIX_CASE4 only): assemble case 4 with the first primitive padded too */
+static int g_fix_case4 = 0;
+void dcol_oracle_set_fix_case4(int on) { g_fix_case4 = on; }
+
 /* primitives/combine_problem_matrices.py:3-70; returns 0 or DCOL_STATUS_UNSUPPORTED (case 4 raises) */
 static int combine_problem_matrices(const prim_blocks* B1, const prim_blocks* B2, conic_problem* P)
 {
     int v1 = B1->v, v2 = B2->v;
-    if (v1 > 4 && v2 > 4) return DCOL_STATUS_UNSUPPORTED; /* np.vstack of ragged widths -> ValueError */
+    if (v1 > 4 && v2 > 4) {
+        if (!g_fix_case4) return DCOL_STATUS_UNSUPPORTED; /* np.vstack of ragged widths -> ValueError */
+        /* columns [x, alpha, extras1, extras2] (lines 58-67 place the second primitive's extras after the
+         * first's; the fix is to pad the first primitive's blocks to the same width) */
+        memset(P, 0, sizeof(*P));
+        int e1 = v1 - 4, e2 = v2 - 4, row = 0;
+        P->n = 4 + e1 + e2; P->n_ort = B1->n_ort + B2->n_ort; P->q1 = B1->n_soc; P->q2 = B2->n_soc;
+        P->m = P->n_ort + P->q1 + P->q2;
+        P->c[3] = 1.0;
+        for (int i = 0; i < B1->n_ort; ++i, ++row) { memcpy(P->G[row], B1->G_ort[i], sizeof(double) * v1); P->h[row] = B1->h_ort[i]; }
+        for (int i = 0; i < B2->n_ort; ++i, ++row) {
+            memcpy(P->G[row], B2->G_ort[i], sizeof(double) * 4);
+            memcpy(P->G[row] + 4 + e1, B2->G_ort[i] + 4, sizeof(double) * e2);
+            P->h[row] = B2->h_ort[i];
+        }
+        for (int i = 0; i < B1->n_soc; ++i, ++row) { memcpy(P->G[row], B1->G_soc[i], sizeof(double) * v1); P->h[row] = B1->h_soc[i]; }
+        for (int i = 0; i < B2->n_soc; ++i, ++row) {
+            memcpy(P->G[row], B2->G_soc[i], sizeof(double) * 4);
+            memcpy(P->G[row] + 4 + e1, B2->G_soc[i] + 4, sizeof(double) * e2);
+            P->h[row] = B2->h_soc[i];
+        }
+        return 0;
+    }
     memset(P, 0, sizeof(*P));
     int n = v1 > v2 ? v1 : v2;
     P->n = n; P->n_ort = B1->n_ort + B2->n_ort; P->q1 = B1->n_soc; P->q2 = B2->n_soc;
@@ -716,7 +753,11 @@ static void obj_val_grad_exact(const dcol_shape* s1, const dcol_shape* s2, const
         /* this primitive's slice of x and z */
         double xk[MAXN] = { x[0], x[1], x[2], x[3] };
         int ne = (sh[k]->type == DCOL_CAPSULE || sh[k]->type == DCOL_CYLINDER) ? 1 : (sh[k]->type == DCOL_POLYGON ? 2 : 0);
-        for (int j = 0; j < ne; ++j) xk[4 + j] = x[4 + j]; /* only one primitive of a supported pair has extras */
+        {
+            int ne1 = (s1->type == DCOL_CAPSULE || s1->type == DCOL_CYLINDER) ? 1 : (s1->type == DCOL_POLYGON ? 2 : 0);
+            int off = (k == 1) ? ne1 : 0; /* the second primitive's extras follow the first's */
+            for (int j = 0; j < ne; ++j) xk[4 + j] = x[4 + off + j];
+        }
         const double* z_ort = z + (k == 0 ? 0 : no1);
         const double* z_soc = z + P->n_ort + (k == 0 ? 0 : P->q1);
         double base_r0 = prim_lagrangian(sh[k], A, b, zero, Qp, xk, z_ort, z_soc);

@@ -44,6 +44,8 @@ def lib(fma: bool = False):
                                         dp, dp, dp, ip, ip]
         L.dcol_oracle_assemble.restype = C.c_int
         L.dcol_oracle_assemble.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip]
+        L.dcol_oracle_set_fix_case4.restype = None
+        L.dcol_oracle_set_fix_case4.argtypes = [C.c_int]
         L.dcol_oracle_dcm.restype = None
         L.dcol_oracle_dcm.argtypes = [dp, dp, dp]
         _lib = _libs[fma] = L
@@ -85,7 +87,7 @@ def solve_pair(records, A, b, i1, i2, pose1, pose2, tol=1e-6, grad_mode=GRAD_FD)
 
 
 def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, grad_mode=GRAD_FD, threads=None,
-                want_contact=True, fma=False):
+                want_contact=True, fma=False, fix_case4=False):
     """Batch -> dict(alpha[B], contact[B,3], grad[B,12], iters[B], status[B]).
     ``fma=True`` runs the fused-multiply-add build (rounding-sensitivity probe, see Makefile)."""
     records, A, b = _table(records, A, b)
@@ -100,10 +102,12 @@ def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, grad_mode=GRA
     iters = np.empty(B, dtype=np.int32)
     status = np.empty(B, dtype=np.int32)
     null = C.POINTER(C.c_double)()
+    lib(fma).dcol_oracle_set_fix_case4(1 if fix_case4 else 0)   # extension switch, see dcol_oracle.c
     lib(fma).dcol_oracle_batch(records.ctypes.data, _dp(A), _dp(b), _ip(idx1), _ip(idx2), _dp(pose1), _dp(pose2), B,
                             float(tol), int(grad_mode), int(threads or os.cpu_count() or 1), _dp(alpha),
                             _dp(contact) if contact is not None else null, _dp(grad) if grad is not None else null,
                             _ip(iters), _ip(status))
+    lib(fma).dcol_oracle_set_fix_case4(0)
     return dict(alpha=alpha, contact=contact, grad=grad, iters=iters, status=status)
 
 

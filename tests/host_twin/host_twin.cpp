@@ -55,12 +55,15 @@ struct RunOne {
     }
 };
 
+int g_fix_case4 = 0; /* mirrors the DCOL_FIX_CASE4 flag of the C ABI */
+
 void run_pair(const PairIn& in, PairOut& out, bool trace)
 {
     for (int i = 0; i <= DCOL_MAX_ITER; ++i) out.mu[i] = NAN;
     int c1 = shape_class(*in.s1, in.A), c2 = shape_class(*in.s2, in.A);
     RunOne f = { &in, &out, trace };
-    if (c1 < 0 || c2 < 0 || !dispatch_classes(c1, c2, f)) {
+    const bool allowed = c1 >= 0 && c2 >= 0 && (g_fix_case4 || class_pair_supported(c1, c2));
+    if (!allowed || !dispatch_classes(c1, c2, f)) {
         out.status = DCOL_STATUS_UNSUPPORTED;
         out.iters = 0;
         out.alpha = NAN;
@@ -104,6 +107,8 @@ void* worker(void* arg)
 }
 
 } /* namespace */
+
+extern "C" void dcol_twin_set_fix_case4(int on) { g_fix_case4 = on; }
 
 extern "C" int dcol_twin_batch(const dcol_shape* shapes, const double* A, const double* b, const int32_t* idx1,
                                const int32_t* idx2, const double* pose1, const double* pose2, int64_t B, double tol,

@@ -60,7 +60,8 @@ def _table(records, A, b):
     return records, A, b
 
 
-def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, max_iter=50, threads=None, want_grad=True):
+def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, max_iter=50, threads=None, want_grad=True,
+                fix_case4=False):
     records, A, b = _table(records, A, b)
     idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
     idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
@@ -70,9 +71,11 @@ def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, max_iter=50, 
     alpha, contact = np.empty(B), np.empty((B, 3))
     grad = np.empty((B, 12)) if want_grad else None
     iters, status = np.empty(B, np.int32), np.empty(B, np.int32)
+    lib().dcol_twin_set_fix_case4(1 if fix_case4 else 0)
     lib().dcol_twin_batch(records.ctypes.data, _dp(A), _dp(b), _ip(idx1), _ip(idx2), _dp(pose1), _dp(pose2), B,
                           float(tol), int(max_iter), int(threads or os.cpu_count() or 1), _dp(alpha), _dp(contact),
                           _dp(grad) if want_grad else C.POINTER(C.c_double)(), _ip(iters), _ip(status))
+    lib().dcol_twin_set_fix_case4(0)
     return dict(alpha=alpha, contact=contact, grad=grad, iters=iters, status=status)
 
 
