@@ -517,13 +517,15 @@ struct Solver {
      * Unblocked, pivot test `<= 0` with NaN passing, as OpenBLAS potf2 behind numpy/scipy. */
     DCOL_HD static int chol(const double (&M)[N][N], double (&L)[N][N], double (&Li)[N])
     {
+        int status = 0;
         DCOL_UNROLL
         for (int j = 0; j < N; ++j) {
             double d = M[j][j];
             DCOL_UNROLL
             for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-            /* a non-finite entry of M reaches a pivot as NaN (or as +inf, whose rsqrt poisons the solve) */
-            if (!(d > 0.0)) return (d != d) ? DCOL_STATUS_NON_FINITE : DCOL_STATUS_NOT_PD;
+            /* Branch-free (one basic block for the scheduler): the FIRST bad pivot decides the status, as the
+             * early exits of potf2 / check_finite would; a non-finite entry of M reaches a pivot as NaN */
+            if (status == 0 && !(d > 0.0)) status = (d != d) ? DCOL_STATUS_NON_FINITE : DCOL_STATUS_NOT_PD;
             const double ri = rsqrt_(d);
             L[j][j] = d * ri;
             Li[j] = ri;
@@ -535,7 +537,7 @@ struct Solver {
                 L[i][j] = v * ri;
             }
         }
-        return 0;
+        return status;
     }
     DCOL_HD static void chol_solve(const double (&L)[N][N], const double (&Li)[N], double (&v)[N])
     {
@@ -977,6 +979,11 @@ struct Solver {
             double bad = 0.0;
             double sz = nt_and_mu<P1>(c1, b1, bad);
             sz += nt_and_mu<P2>(c2, b2, bad);
+            if (nonfinite_probe(sz) != 0.0) {
+                /* the previous step left a non-finite iterate: the reference's check_finite raised inside it */
+                res.iters = it > 0 ? it - 1 : 0;
+                return res.status = DCOL_STATUS_NON_FINITE;
+            }
             if (bad != 0.0) return res.status = DCOL_STATUS_NON_FINITE; /* cho_factor(W_soc) check_finite */
             const double mu = sz * ideg;
             if (trace && trace->mu) trace->mu[it] = mu;
@@ -997,7 +1004,6 @@ struct Solver {
             for (int j = 0; j < N; ++j) dx[j] = va[j]; /* bx + G~^T b~ */
             if (int bad = chol(M, L, Li)) return res.status = bad; /* scipy cholesky: check_finite, LinAlgError */
             chol_solve(L, Li, dx);
-            if (probe_vec(dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
 
             /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
             double tm[2] = { 0.0, 0.0 }, d_l = 0.0, d_sz = 0.0, vk[N];
@@ -1015,7 +1021,6 @@ struct Solver {
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) dx[j] = va[j] + vk[j] - sigmu * vl[j];
             chol_solve(L, Li, dx);
-            if (probe_vec(dx) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
             tm[0] = 0.0;
             tm[1] = 0.0;
             pass_c<P1>(p1, c1, CE1, b1, dx, sigmu, tm);
@@ -1028,6 +1033,10 @@ struct Solver {
             pass_d<P2>(c2, b2, a);
         }
         res.iters = max_iter;
+        if (probe_vec(x) != 0.0) { /* the last step itself went non-finite */
+            res.iters = max_iter - 1;
+            return res.status = DCOL_STATUS_NON_FINITE;
+        }
         return res.status = DCOL_STATUS_MAX_ITER; /* pdip.py:470 */
     }
 
