@@ -125,7 +125,8 @@ def cpu_baseline(n_target_seconds=12.0, threads=None, seed=1234):
     assert int((r["status"] != 0).sum()) == 0
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {n} pairs of the config-4 batch (seed {seed}), oracle/dcol_oracle.c with the reference's "
-                      f"13-evaluation finite-difference gradient, {threads} POSIX threads, {dt:.1f} s"}
+                      f"13-evaluation finite-difference gradient, {threads} POSIX threads, {dt:.1f} s; the Python reference "
+                      f"itself runs ~1e2 calls/s/core (BASELINE.md section 2), this C port ~6e4"}
 
 
 def run_reference(args):
@@ -323,6 +324,8 @@ def main():
             "config": {"workload": WORKLOAD if args.workload == "config4" else WORKLOAD5, "pairs_per_gpu": B, "type_pairs": plans[0].n_groups,
                        "mean_pdip_iters": float(iters.mean()), "failed_pairs": n_fail,
                        "l2": "inputs larger than L2 (805 MB of poses per step at the default size)",
+                       "plan": "pairs grouped by shape pair once (device counting sort), plan reused by every step, as ALTRO "
+                               "re-evaluates a fixed pair list; the e2e figure re-plans every chunk",
                        "collective": {"none": "none",
                                       "fused": "all-gather fused into the solve: the kernel epilogue stores each 112 B record "
                                                "(alpha, grad[12], iters, status) to every rank's buffer over NVLink peer "

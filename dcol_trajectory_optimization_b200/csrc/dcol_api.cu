@@ -540,7 +540,7 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
         if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
     }
-    int64_t kChunk = 1 << 20;
+    int64_t kChunk = 1 << 19; /* measured on B200 + PCIe 5: 2^19 pairs (50 MB in, 75 MB out) gives the best overlap */
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
     for (int i = 0; i < 2; ++i) {
