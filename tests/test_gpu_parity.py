@@ -296,3 +296,20 @@ def test_peer_record_gather_two_gpus():
                         os.path.join(root, "tests", "mgpu_peer_gather.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("PEER_GATHER_OK") == 2
+
+
+def test_proximity_batch_convenience_and_pinned_buffers(dcol):
+    """proximity_batch over lists of primitive objects (shared objects -> shared shape records) and the
+    page-locked buffer helpers."""
+    box, sph, cone = dcol.create_rect_prism(1, 2, 3), dcol.SphereMRP(0.5), dcol.ConeMRP(2.0, np.deg2rad(22))
+    sph.r = np.array([3.0, 1.0, -0.5])
+    cone.r, cone.p = np.array([0.5, -4.0, 1.0]), np.array([0.1, 0.2, -0.1])
+    res = dcol.proximity_batch([box, box, sph], [sph, cone, cone])
+    from dcol_trajectory_optimization_b200.proximity import proximity_gradient
+    for k, (a, b) in enumerate([(box, sph), (box, cone), (sph, cone)]):
+        alpha, g = proximity_gradient(a, b)
+        assert res.status[k] == 0 and res.alpha[k] == alpha and np.array_equal(res.grad[k], g)
+    buf = dcol.pinned_empty((1000, 6))
+    buf[:] = 1.5
+    assert buf.shape == (1000, 6) and buf.dtype == np.float64 and float(buf.sum()) == 9000.0
+    dcol.pinned_free(buf)
