@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid
     const int st = sv.solve(a.c1, a.c2, pose1, pose2, a.b.tol, a.b.max_iter, want_grad, res, &tr);
     const double alpha = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
     if (a.b.flags & DCOL_WANT_CONTACT) {
+        double cp[3] = { nan, nan, nan };
+        if (st == DCOL_STATUS_OK) sv.contact_point(a.c1, a.c2, pose1, pose2, cp);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = st == DCOL_STATUS_OK ? sv.x[j] : nan; /* proximity.py:52 */
+        for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = cp[j]; /* proximity.py:52 */
     }
     double g[12];
     if (want_grad) {
@@ -148,11 +150,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid
         TraceOut* out = a.b.trace;
         out->n = S::N;
         for (int j = 0; j < 8; ++j) out->x[j] = nan;
-        if (st == DCOL_STATUS_OK) {
-#pragma unroll
-            for (int j = 0; j < S::N; ++j) out->x[j] = sv.x[j];
-        }
-        out->m = st == DCOL_STATUS_OK ? sv.export_sz(a.c1, a.c2, out->s, out->z) : 0;
+        out->m = st == DCOL_STATUS_OK ? sv.export_xsz(a.c1, a.c2, pose1, pose2, out->x, out->s, out->z) : 0;
     }
 }
 

@@ -38,6 +38,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/dcol.h"
 
 #if defined(__CUDACC__)
@@ -178,9 +180,13 @@ struct ShapeConst {
  * polytope, but each has two non-zeros (+-y_k, -b_i alpha), known at compile time. */
 constexpr int KIND_BOX = 100;
 
-template <int KIND, int FC>
+/* IDENT: the solver's working frame IS this primitive's body frame (Q' = I, r' = 0 are not stored and
+ * every rotation / translation of this primitive's local vectors disappears at compile time). */
+template <int KIND, int FC, bool IDENT = false>
 struct Prim {
     static constexpr int kind = KIND;
+    static constexpr int fc = FC;
+    static constexpr bool ident = IDENT;
     static constexpr bool has_faces = (KIND == DCOL_POLYTOPE || KIND == DCOL_POLYGON || KIND == KIND_BOX);
     static constexpr bool dyn = has_faces && FC == 0;                       /* runtime face count      */
     static constexpr int FMAX = has_faces ? (FC ? FC : DCOL_MAX_FACES) : 0; /* sized for               */
@@ -191,9 +197,11 @@ struct Prim {
     static constexpr int NE = (KIND == DCOL_CAPSULE || KIND == DCOL_CYLINDER) ? 1 : (KIND == DCOL_POLYGON ? 2 : 0);
     static constexpr int NL = 4 + NE;
     static constexpr bool rot = KIND != DCOL_SPHERE;  /* the sphere's rows are written in world axes */
+    static constexpr bool frot = rot && !IDENT;       /* local vectors are rotated by Qp                */
     static constexpr bool ball = Q == 4 && KIND != DCOL_ELLIPSOID; /* soc rows (-R alpha, -y + E e), world-frame duals */
     typedef ShapeConst<FMAX> Const;
     typedef Prim P;
+    typedef Prim<KIND, FC, true> Ident; /* the same primitive as the solver's frame */
 
     double Qp[3][3]; /* Q' = Q(p) Q_offset                  */
     double rp[3];    /* r' = r + Q(p) r_offset              */
@@ -254,15 +262,36 @@ struct Prim {
         }
     }
 
+    /* this primitive's pose expressed in the frame (Qf, rf) of the other one:  Q' <- Qf^T Q',  r' <- Qf^T (r' - rf) */
+    DCOL_HD void make_relative(const double (&Qf)[3][3], const double (&rf)[3])
+    {
+        double d[3], Qn[3][3];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) d[i] = rp[i] - rf[i];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            rp[i] = Qf[0][i] * d[0] + Qf[1][i] * d[1] + Qf[2][i] * d[2];
+            DCOL_UNROLL
+            for (int j = 0; j < 3; ++j) Qn[i][j] = Qf[0][i] * Qp[0][j] + Qf[1][i] * Qp[1][j] + Qf[2][i] * Qp[2][j];
+        }
+        if (rot) {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) Qp[i][j] = Qn[i][j];
+            }
+        }
+    }
+
     /* world vector v[N] -> local xh[NL];  AFFINE subtracts r' (points), otherwise directions */
     template <int N, bool AFFINE>
     DCOL_HD void to_local(const double (&v)[N], int col_e, double (&xh)[NL]) const
     {
         double d[3];
         DCOL_UNROLL
-        for (int i = 0; i < 3; ++i) d[i] = AFFINE ? v[i] - rp[i] : v[i];
+        for (int i = 0; i < 3; ++i) d[i] = (AFFINE && !IDENT) ? v[i] - rp[i] : v[i];
         DCOL_UNROLL
-        for (int j = 0; j < 3; ++j) xh[j] = rot ? (Qp[0][j] * d[0] + Qp[1][j] * d[1] + Qp[2][j] * d[2]) : d[j];
+        for (int j = 0; j < 3; ++j) xh[j] = frot ? (Qp[0][j] * d[0] + Qp[1][j] * d[1] + Qp[2][j] * d[2]) : d[j];
         xh[3] = v[3];
         DCOL_UNROLL
         for (int j = 0; j < NE; ++j) xh[4 + j] = v[col_e + j];
@@ -273,7 +302,7 @@ struct Prim {
     {
         DCOL_UNROLL
         for (int i = 0; i < 3; ++i)
-            out[i] += rot ? (Qp[i][0] * acc[0] + Qp[i][1] * acc[1] + Qp[i][2] * acc[2]) : acc[i];
+            out[i] += frot ? (Qp[i][0] * acc[0] + Qp[i][1] * acc[1] + Qp[i][2] * acc[2]) : acc[i];
         out[3] += acc[3];
         DCOL_UNROLL
         for (int j = 0; j < NE; ++j) out[col_e + j] += acc[4 + j];
@@ -282,7 +311,7 @@ struct Prim {
     template <int N>
     DCOL_HD void gram_from_local(const double (&Gl)[NL][NL], int col_e, double (&M)[N][N]) const
     {
-        if (rot) {
+        if (frot) {
             double T[3][3]; /* T = Q' Gl_yy */
             DCOL_UNROLL
             for (int i = 0; i < 3; ++i) {
@@ -506,12 +535,22 @@ struct Solver {
     static constexpr int CE1 = 4, CE2 = 4 + P1::NE;
     typedef typename P1::Const C1;
     typedef typename P2::Const C2;
+    /* The solve runs in the body frame of the FIRST primitive: x~ = Q1'^T (x - r1').  The map is an orthogonal
+     * change of the first three unknowns, under which the least-squares start, the Newton steps and even the
+     * diag-only triangular solve of the dual start (it only involves the Schur complement of the x-block) are
+     * invariant, so (s, z, alpha, extras) follow the same path; the first primitive then needs no rotation or
+     * translation at all, and the second one carries its pose relative to the first. */
+    /* ... unless the first primitive is a sphere (its rows need no rotation anyway) and the second is not:
+     * then the second primitive's body frame is the working frame. */
+    static constexpr bool kFrame2 = !P1::rot && P2::rot;
+    typedef typename std::conditional<kFrame2, P1, typename P1::Ident>::type F1;
+    typedef typename std::conditional<kFrame2, typename P2::Ident, P2>::type F2;
 
-    P1 p1;
-    P2 p2;
-    Block<P1> b1;
-    Block<P2> b2;
-    double x[N];
+    F1 p1;
+    F2 p2;
+    Block<F1> b1;
+    Block<F2> b2;
+    double x[N]; /* (x~, alpha, extras) */
 
     /* ---- lower Cholesky of the symmetric M (upper triangle valid); Li holds 1/L_jj.
      * Unblocked, pivot test `<= 0` with NaN passing, as OpenBLAS potf2 behind numpy/scipy. */
@@ -878,14 +917,16 @@ struct Solver {
     }
 
     /* ---- gradient share of one primitive: d/d(r, p) of z^T (G(theta) x - h(theta)), (x, z) frozen.
-     * proximity_gradient.py:8-88 by the chain rule instead of finite differences. */
-    template <class P>
-    DCOL_HD void grad_block(const P& p, const typename P::Const& c, int col_e, const Block<P>& B, const double pm[3],
-                            const double Qm[3][3], double* g6) const
+     * proximity_gradient.py:8-88 by the chain rule instead of finite differences.  pw: the primitive at its
+     * WORLD pose; xw: the solution in world coordinates; Rf: rotation of the working frame (world pose of the
+     * first primitive), which carries the cone components of a primitive whose rows are not rotated (sphere). */
+    template <class P, class BL>
+    DCOL_HD static void grad_block(const P& pw, const typename P::Const& c, int col_e, const BL& B, const double (&xw)[N],
+                                   const double (&Rf)[3][3], const double pm[3], const double Qm[3][3], double* g6)
     {
         /* u = y-part of the local adjoint product of the rows whose coefficients are constant in the body
-         * frame (all orthant rows, the cone's soc rows); the ball soc rows -(x - r') + Q' E e are written in
-         * world axes by the reference, so their dual is frozen in world components: zw = Q' z_v. */
+         * frame (all orthant rows, the cone's and the ellipsoid's soc rows); the ball soc rows -(x - r') + Q' E e
+         * are written in world axes by the reference, so their dual is frozen in world components: zw. */
         double acc[P::NL];
         DCOL_UNROLL
         for (int j = 0; j < P::NL; ++j) acc[j] = 0.0;
@@ -893,19 +934,20 @@ struct Solver {
         if (P::Q > 0 && !P::ball) P::soc_apply_t(c, B.zq, acc);
         double d[3], gr[3], Mq[3][3];
         DCOL_UNROLL
-        for (int i = 0; i < 3; ++i) d[i] = x[i] - p.rp[i];
+        for (int i = 0; i < 3; ++i) d[i] = xw[i] - pw.rp[i];
         /* gr = dL/dr' = -Q' u (+ zw);  Mq = dL/dQ(p) = d (Q_off u)^T + zw (Q_off ehat)^T + gr r_off^T */
         double zw[3] = { 0.0, 0.0, 0.0 }, eh[3] = { 0.0, 0.0, 0.0 };
         if (P::ball) {
             DCOL_UNROLL
             for (int i = 0; i < 3; ++i)
-                zw[i] = P::rot ? (p.Qp[i][0] * B.zq[1] + p.Qp[i][1] * B.zq[2] + p.Qp[i][2] * B.zq[3]) : B.zq[1 + i];
+                zw[i] = P::rot ? (pw.Qp[i][0] * B.zq[1] + pw.Qp[i][1] * B.zq[2] + pw.Qp[i][2] * B.zq[3])
+                               : (Rf[i][0] * B.zq[1] + Rf[i][1] * B.zq[2] + Rf[i][2] * B.zq[3]);
             DCOL_UNROLL
-            for (int j = 0; j < P::NE; ++j) eh[j] = x[col_e + j];
+            for (int j = 0; j < P::NE; ++j) eh[j] = xw[col_e + j];
         }
         DCOL_UNROLL
         for (int i = 0; i < 3; ++i)
-            gr[i] = zw[i] - (P::rot ? (p.Qp[i][0] * acc[0] + p.Qp[i][1] * acc[1] + p.Qp[i][2] * acc[2]) : acc[i]);
+            gr[i] = zw[i] - (P::rot ? (pw.Qp[i][0] * acc[0] + pw.Qp[i][1] * acc[1] + pw.Qp[i][2] * acc[2]) : acc[i]);
         double qu[3], qe[3];
         DCOL_UNROLL
         for (int i = 0; i < 3; ++i) {
@@ -927,11 +969,16 @@ struct Solver {
     DCOL_HD int solve(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double tol, int max_iter,
                       bool want_grad, PairResult<N>& res, const Trace* trace)
     {
-        double Q1[3][3], Q2[3][3];
-        dcm_from_mrp(pose1 + 3, Q1);
-        dcm_from_mrp(pose2 + 3, Q2);
-        p1.set_pose(c1, pose1, Q1);
-        p2.set_pose(c2, pose2, Q2);
+        {
+            double Q1[3][3], Q2[3][3];
+            dcm_from_mrp(pose1 + 3, Q1);
+            dcm_from_mrp(pose2 + 3, Q2);
+            P1 w1; /* world poses; one of them is the working frame, the other becomes relative to it */
+            P2 w2;
+            w1.set_pose(c1, pose1, Q1);
+            w2.set_pose(c2, pose2, Q2);
+            set_relative(w1, w2);
+        }
         res.iters = 0;
 
         double L[N][N], Li[N];
@@ -944,15 +991,15 @@ struct Solver {
                 DCOL_UNROLL
                 for (int j = 0; j < N; ++j) M[i][j] = 0.0;
             }
-            init_accumulate<P1>(p1, c1, CE1, M, gth);
-            init_accumulate<P2>(p2, c2, CE2, M, gth);
+            init_accumulate<F1>(p1, c1, CE1, M, gth);
+            init_accumulate<F2>(p2, c2, CE2, M, gth);
             if (int bad = chol(M, L, Li)) return res.status = bad; /* numpy cholesky -> LinAlgError; check_finite */
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) x[j] = gth[j];
             chol_solve(L, Li, x); /* x_hat = (G^T G)^-1 G^T h */
             if (probe_vec(x) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
-            rows<P1, true>(p1, c1, CE1, x, b1.so, b1.sq);
-            rows<P2, true>(p2, c2, CE2, x, b2.so, b2.sq); /* s~ = G x_hat - h */
+            rows<F1, true>(p1, c1, CE1, x, b1.so, b1.sq);
+            rows<F2, true>(p2, c2, CE2, x, b2.so, b2.sq); /* s~ = G x_hat - h */
             /* solve_triangular(F, -c) reads the UPPER triangle of the lower factor, i.e. its diagonal
              * (pdip.py:326); then a proper back substitution with F^T */
             double xd[N];
@@ -965,8 +1012,8 @@ struct Solver {
                 for (int k = i + 1; k < N; ++k) t -= L[k][i] * xd[k];
                 xd[i] = t * Li[i];
             }
-            rows<P1, false>(p1, c1, CE1, xd, b1.zo, b1.zq);
-            rows<P2, false>(p2, c2, CE2, xd, b2.zo, b2.zq); /* z~ = G x */
+            rows<F1, false>(p1, c1, CE1, xd, b1.zo, b1.zq);
+            rows<F2, false>(p2, c2, CE2, xd, b2.zo, b2.zq); /* z~ = G x */
             bring2cone<0>(c1, c2);
             bring2cone<1>(c1, c2);
         }
@@ -977,8 +1024,8 @@ struct Solver {
         for (int it = 0; it < max_iter; ++it) {
             res.iters = it;
             double bad = 0.0;
-            double sz = nt_and_mu<P1>(c1, b1, bad);
-            sz += nt_and_mu<P2>(c2, b2, bad);
+            double sz = nt_and_mu<F1>(c1, b1, bad);
+            sz += nt_and_mu<F2>(c2, b2, bad);
             if (nonfinite_probe(sz) != 0.0) {
                 /* the previous step left a non-finite iterate: the reference's check_finite raised inside it */
                 res.iters = it > 0 ? it - 1 : 0;
@@ -997,8 +1044,8 @@ struct Solver {
                 DCOL_UNROLL
                 for (int j = 0; j < N; ++j) M[i][j] = 0.0;
             }
-            pass_a<P1>(p1, c1, CE1, b1, x, M, va, vl);
-            pass_a<P2>(p2, c2, CE2, b2, x, M, va, vl);
+            pass_a<F1>(p1, c1, CE1, b1, x, M, va, vl);
+            pass_a<F2>(p2, c2, CE2, b2, x, M, va, vl);
             double dx[N];
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) dx[j] = va[j]; /* bx + G~^T b~ */
@@ -1009,8 +1056,8 @@ struct Solver {
             double tm[2] = { 0.0, 0.0 }, d_l = 0.0, d_sz = 0.0, vk[N];
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) vk[j] = 0.0;
-            pass_b<P1>(p1, c1, CE1, b1, dx, tm, d_l, d_sz, vk);
-            pass_b<P2>(p2, c2, CE2, b2, dx, tm, d_l, d_sz, vk);
+            pass_b<F1>(p1, c1, CE1, b1, dx, tm, d_l, d_sz, vk);
+            pass_b<F2>(p2, c2, CE2, b2, dx, tm, d_l, d_sz, vk);
             double t = max_(tm[0], tm[1]);
             double a = t > 1.0 ? rcp_(t) : 1.0;
             const double rho = (sz + a * d_l + (a * a) * d_sz) * rcp_(sz);
@@ -1023,14 +1070,14 @@ struct Solver {
             chol_solve(L, Li, dx);
             tm[0] = 0.0;
             tm[1] = 0.0;
-            pass_c<P1>(p1, c1, CE1, b1, dx, sigmu, tm);
-            pass_c<P2>(p2, c2, CE2, b2, dx, sigmu, tm);
+            pass_c<F1>(p1, c1, CE1, b1, dx, sigmu, tm);
+            pass_c<F2>(p2, c2, CE2, b2, dx, sigmu, tm);
             t = max_(tm[0], tm[1]);
             a = min_(1.0, 0.99 * (t > 1.0 ? rcp_(t) : 1.0)); /* pdip.py:462 */
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) x[j] += a * dx[j];
-            pass_d<P1>(c1, b1, a);
-            pass_d<P2>(c2, b2, a);
+            pass_d<F1>(c1, b1, a);
+            pass_d<F2>(c2, b2, a);
         }
         res.iters = max_iter;
         if (probe_vec(x) != 0.0) { /* the last step itself went non-finite */
@@ -1045,44 +1092,104 @@ struct Solver {
     {
         double alpha = -1.0, mn = INFINITY;
         bool any = false;
-        b2c_scan<P1, SEL>(c1, b1, any, mn);
-        b2c_scan<P2, SEL>(c2, b2, any, mn);
+        b2c_scan<F1, SEL>(c1, b1, any, mn);
+        b2c_scan<F2, SEL>(c2, b2, any, mn);
         if (any) alpha = -mn;
-        b2c_soc<P1, SEL>(b1, alpha);
-        b2c_soc<P2, SEL>(b2, alpha);
+        b2c_soc<F1, SEL>(b1, alpha);
+        b2c_soc<F2, SEL>(b2, alpha);
         if (alpha < 0.0) return;
-        b2c_shift<P1, SEL>(c1, b1, 1.0 + alpha);
-        b2c_shift<P2, SEL>(c2, b2, 1.0 + alpha);
+        b2c_shift<F1, SEL>(c1, b1, 1.0 + alpha);
+        b2c_shift<F2, SEL>(c2, b2, 1.0 + alpha);
+    }
+
+    DCOL_HD void set_relative(const P1& w1, const P2& w2)
+    {
+        if constexpr (kFrame2) {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                p1.rp[i] = w1.rp[i];
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) p1.Qp[i][j] = w1.Qp[i][j];
+            }
+            p1.make_relative(w2.Qp, w2.rp);
+        } else {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                p2.rp[i] = w2.rp[i];
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) p2.Qp[i][j] = w2.Qp[i][j];
+            }
+            p2.make_relative(w1.Qp, w1.rp);
+        }
+    }
+
+    /* the solution in world coordinates: x = Qf x~ + rf (alpha and the extras are frame independent) */
+    DCOL_HD void world_frames(const C1& c1, const C2& c2, const double* pose1, const double* pose2, P1& w1, P2& w2,
+                              double (&Q1)[3][3], double (&Q2)[3][3], double (&xw)[N]) const
+    {
+        dcm_from_mrp(pose1 + 3, Q1);
+        dcm_from_mrp(pose2 + 3, Q2);
+        w1.set_pose(c1, pose1, Q1);
+        w2.set_pose(c2, pose2, Q2);
+        const double (&Qf)[3][3] = kFrame2 ? w2.Qp : w1.Qp;
+        const double (&rf)[3] = kFrame2 ? w2.rp : w1.rp;
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) xw[i] = rf[i] + (Qf[i][0] * x[0] + Qf[i][1] * x[1] + Qf[i][2] * x[2]);
+        DCOL_UNROLL
+        for (int j = 3; j < N; ++j) xw[j] = x[j];
+    }
+
+    /* contact point x[0:3] in world coordinates (proximity.py:52) */
+    DCOL_HD void contact_point(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double (&out)[3]) const
+    {
+        double Qm[3][3];
+        dcm_from_mrp((kFrame2 ? pose2 : pose1) + 3, Qm);
+        typename std::conditional<kFrame2, P2, P1>::type wf;
+        if constexpr (kFrame2) wf.set_pose(c2, pose2, Qm);
+        else wf.set_pose(c1, pose1, Qm);
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) out[i] = wf.rp[i] + (wf.Qp[i][0] * x[0] + wf.Qp[i][1] * x[1] + wf.Qp[i][2] * x[2]);
     }
 
     DCOL_HD void gradient(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double* grad) const
     {
-        double Q1[3][3], Q2[3][3];
-        dcm_from_mrp(pose1 + 3, Q1);
-        dcm_from_mrp(pose2 + 3, Q2);
-        grad_block<P1>(p1, c1, CE1, b1, pose1 + 3, Q1, grad);
-        grad_block<P2>(p2, c2, CE2, b2, pose2 + 3, Q2, grad + 6);
+        double Q1[3][3], Q2[3][3], xw[N];
+        P1 w1;
+        P2 w2;
+        world_frames(c1, c2, pose1, pose2, w1, w2, Q1, Q2, xw);
+        const double (&Rf)[3][3] = kFrame2 ? w2.Qp : w1.Qp;
+        grad_block<P1>(w1, c1, CE1, b1, xw, Rf, pose1 + 3, Q1, grad);
+        grad_block<P2>(w2, c2, CE2, b2, xw, Rf, pose2 + 3, Q2, grad + 6);
     }
 
-    /* world-frame (s, z) in the reference's row order [ort1; ort2; soc1; soc2] (debug entry point) */
+    /* world-frame (x, s, z) in the reference's row order [ort1; ort2; soc1; soc2] (debug entry point) */
     template <class P>
-    DCOL_HD static void export_soc(const P& p, const double (&q)[P::QA], double* out)
+    DCOL_HD static void export_soc(const P& pw, const double (&Rf)[3][3], const double (&q)[P::QA], double* out)
     {
         if (P::Q == 0) return;
-        if (P::ball && P::rot) {
+        if (P::ball) { /* the reference keeps these cone components in world axes */
             out[0] = q[0];
-            for (int i = 0; i < 3; ++i) out[1 + i] = p.Qp[i][0] * q[1] + p.Qp[i][1] * q[2] + p.Qp[i][2] * q[3];
+            for (int i = 0; i < 3; ++i)
+                out[1 + i] = P::rot ? (pw.Qp[i][0] * q[1] + pw.Qp[i][1] * q[2] + pw.Qp[i][2] * q[3])
+                                    : (Rf[i][0] * q[1] + Rf[i][1] * q[2] + Rf[i][2] * q[3]);
         } else {
             for (int i = 0; i < P::Q; ++i) out[i] = q[i];
         }
     }
-    DCOL_HD int export_sz(const C1& c1, const C2& c2, double* s, double* z) const
+    DCOL_HD int export_xsz(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double* xout, double* s,
+                           double* z) const
     {
+        double Q1[3][3], Q2[3][3], xw[N];
+        P1 w1;
+        P2 w2;
+        world_frames(c1, c2, pose1, pose2, w1, w2, Q1, Q2, xw);
+        for (int j = 0; j < N; ++j) xout[j] = xw[j];
         int r = 0;
         for (int i = 0; i < P1::n_ort(c1); ++i, ++r) { s[r] = b1.so[i]; z[r] = b1.zo[i]; }
         for (int i = 0; i < P2::n_ort(c2); ++i, ++r) { s[r] = b2.so[i]; z[r] = b2.zo[i]; }
-        export_soc<P1>(p1, b1.sq, s + r); export_soc<P1>(p1, b1.zq, z + r); r += P1::Q;
-        export_soc<P2>(p2, b2.sq, s + r); export_soc<P2>(p2, b2.zq, z + r); r += P2::Q;
+        const double (&Rf)[3][3] = kFrame2 ? w2.Qp : w1.Qp;
+        export_soc<P1>(w1, Rf, b1.sq, s + r); export_soc<P1>(w1, Rf, b1.zq, z + r); r += P1::Q;
+        export_soc<P2>(w2, Rf, b2.sq, s + r); export_soc<P2>(w2, Rf, b2.zq, z + r); r += P2::Q;
         return r;
     }
 };

@@ -47,10 +47,10 @@ struct RunOne {
         out->iters = res.iters;
         out->n = S::N;
         out->alpha = st == 0 ? sv->x[3] : NAN;
-        for (int j = 0; j < S::N; ++j) out->x[j] = st == 0 ? sv->x[j] : NAN;
+        for (int j = 0; j < 8; ++j) out->x[j] = NAN;
         for (int j = 0; j < 12; ++j) out->grad[j] = NAN;
         if (st == 0 && in->want_grad) sv->gradient(c1, c2, in->pose1, in->pose2, out->grad);
-        out->m = st == 0 ? sv->export_sz(c1, c2, out->s, out->z) : 0;
+        out->m = st == 0 ? sv->export_xsz(c1, c2, in->pose1, in->pose2, out->x, out->s, out->z) : 0;
         delete sv;
     }
 };
