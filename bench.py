@@ -337,7 +337,7 @@ def main():
             "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,
-                         "traffic": {"dram_bytes_per_launch": 139.9e6, "pairs_per_launch": 209715,
+                         "traffic": {"dram_bytes_per_launch": 143.6e6, "pairs_per_launch": 209715,
                                      "source": "profiles/r01_ncu_full_14kernels.md (ncu --set full, mean of 14 specialisations "
                                                "at this size; algorithmic 236 B/pair = 49.5e6 B per launch)"},
                          "kernel": f"dcol::pair_kernel<P1,P2> ({plans[0].n_groups} specialisations, {n_launches} launches per step)",
