@@ -92,7 +92,7 @@ struct dcol_shape_table {
     std::vector<double> A, b;
     /* group launches of one solve fan out over side streams (fork/join on the caller's stream), so the
      * tail of one group's grid overlaps the head of the next and small groups run concurrently */
-    static constexpr int kSide = 8;
+    static constexpr int kSide = 32;
     std::mutex launch_mu;
     cudaStream_t side[kSide] = {};
     cudaEvent_t fork_ev = nullptr, join_ev[kSide] = {};
@@ -477,7 +477,8 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
     DCOL_DEVICE(T->device);
     (void)cudaGetLastError(); /* drop a stale error left by another library in this process */
     const int n_groups = (int)P->groups.size();
-    const int n_side = n_groups > 1 ? std::min(n_groups, (int)dcol_shape_table::kSide) : 0;
+    static const int side_limit = getenv("DCOL_SIDE_STREAMS") ? std::max(1, std::min(atoi(getenv("DCOL_SIDE_STREAMS")), (int)dcol_shape_table::kSide)) : 8;
+    const int n_side = n_groups > 1 ? std::min(n_groups, side_limit) : 0;
     std::lock_guard<std::mutex> lock(T->launch_mu);
     if (n_side) {
         if (!T->fork_ev) DCOL_CUDA(cudaEventCreateWithFlags(&T->fork_ev, cudaEventDisableTiming));
