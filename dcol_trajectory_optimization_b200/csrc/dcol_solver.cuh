@@ -354,6 +354,34 @@ struct Prim {
         }
     }
 
+    /* one orthant row: value on a local vector, rank-one Gram update, axpy into a local adjoint accumulator
+     * (the passes of the solver fuse these per row so that per-row temporaries die immediately) */
+    DCOL_HD static double row_dot(const Const& c, int i, const double (&xh)[NL])
+    {
+        double t = 0.0;
+        DCOL_UNROLL
+        for (int j = 0; j < NL; ++j)
+            if (nz(i, j)) t += g(c, i, j) * xh[j];
+        return t;
+    }
+    DCOL_HD static void row_gram_add(const Const& c, int i, double w, double (&Gl)[NL][NL])
+    {
+        DCOL_UNROLL
+        for (int j = 0; j < NL; ++j) {
+            if (!nz(i, j)) continue;
+            const double wg = w * g(c, i, j);
+            DCOL_UNROLL
+            for (int k = j; k < NL; ++k)
+                if (nz(i, k)) Gl[j][k] += wg * g(c, i, k);
+        }
+    }
+    DCOL_HD static void row_axpy(const Const& c, int i, double cf, double (&acc)[NL])
+    {
+        DCOL_UNROLL
+        for (int j = 0; j < NL; ++j)
+            if (nz(i, j)) acc[j] += g(c, i, j) * cf;
+    }
+
     /* orthant rows applied to a local vector */
     DCOL_HD static void ort_apply(const Const& c, const double (&xh)[NL], double (&out)[NOA])
     {
@@ -705,29 +733,30 @@ struct Solver {
     DCOL_HD static void pass_a(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&xx)[N],
                                double (&M)[N][N], double (&va)[N], double (&vl)[N])
     {
-        double ro[P::NOA], rq[P::QA];
-        rows<P, true>(p, c, col_e, xx, ro, rq); /* G x - h */
+        double xh[P::NL], rq[P::QA], acc_a[P::NL], acc_l[P::NL];
+        p.template to_local<N, true>(xx, col_e, xh); /* rows of G x - h are constant rows on xh */
+        P::soc_apply(c, xh, rq);
         double Gl[P::NL][P::NL];
         DCOL_UNROLL
         for (int i = 0; i < P::NL; ++i) {
+            acc_a[i] = acc_l[i] = 0.0;
             DCOL_UNROLL
             for (int j = 0; j < P::NL; ++j) Gl[i][j] = 0.0;
         }
-        double w2[P::NOA], ca[P::NOA], cl[P::NOA];
         double qa[P::QA], ql[P::QA];
         const int no = P::n_ort(c);
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
             const double ri = B.rinv[i];
-            const double winv = B.zo[i] * ri;            /* 1 / w_i                       */
-            const double rho = winv * (B.so[i] + ro[i]); /* (W^-1 rz)_i, rz = s + G x - h */
+            const double winv = B.zo[i] * ri;                             /* 1 / w_i                       */
+            const double rho = winv * (B.so[i] + P::row_dot(c, i, xh));   /* (W^-1 rz)_i, rz = s + G x - h */
             B.ta[i] = rho;
-            w2[i] = winv * winv;
-            ca[i] = -(winv * rho);      /* -W^-2 rz: b~_affine = lambda - rho~, and G~^T lambda = G^T z cancels in bx */
-            cl[i] = winv * ri;          /* W^-1 (lambda^-1 o e) */
+            P::row_gram_add(c, i, winv * winv, Gl);
+            /* -W^-2 rz: b~_affine = lambda - rho~, and G~^T lambda = G^T z cancels in bx */
+            P::row_axpy(c, i, -(winv * rho), acc_a);
+            P::row_axpy(c, i, winv * ri, acc_l);                          /* W^-1 (lambda^-1 o e) */
         }
-        P::ort_gram(c, w2, Gl);
         if (P::Q > 0) {
             /* lambda = W z */
             wbar_apply<P::Q>(B.wh, B.bw, -1.0, B.zq, B.eta, B.lam);
@@ -767,9 +796,11 @@ struct Solver {
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, t1, B.ieta, qa);
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, t2, B.ieta, ql);
         }
+        P::soc_apply_t(c, qa, acc_a);
+        P::soc_apply_t(c, ql, acc_l);
         p.template gram_from_local<N>(Gl, col_e, M);
-        rows_t<P>(p, c, col_e, ca, qa, va);
-        rows_t<P>(p, c, col_e, cl, ql, vl);
+        p.template from_local_add<N>(acc_a, col_e, va);
+        p.template from_local_add<N>(acc_l, col_e, vl);
     }
 
     /* ---- line-search measure of a scaled direction against lambda: the step is 1/t for t > 1.
@@ -797,9 +828,11 @@ struct Solver {
     DCOL_HD static void pass_b(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
                                double (&tm)[2], double& d_l, double& d_sz, double (&vk)[N])
     {
-        double ro[P::NOA], rq[P::QA];
-        rows<P, false>(p, c, col_e, dx, ro, rq); /* G dx */
-        double ck[P::NOA], qk[P::QA];
+        double xh[P::NL], rq[P::QA], acc_k[P::NL], qk[P::QA];
+        p.template to_local<N, false>(dx, col_e, xh); /* G dx */
+        P::soc_apply(c, xh, rq);
+        DCOL_UNROLL
+        for (int i = 0; i < P::NL; ++i) acc_k[i] = 0.0;
         const int no = P::n_ort(c);
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
@@ -807,7 +840,7 @@ struct Solver {
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;
             const double lam = (B.so[i] * B.zo[i]) * ri;
-            const double dz = winv * ro[i] - (lam - B.ta[i]); /* dz~ = G~ dx - b~ */
+            const double dz = winv * P::row_dot(c, i, xh) - (lam - B.ta[i]); /* dz~ = G~ dx - b~ */
             const double ds = -lam - dz;                      /* ds~ = d - dz~, d = -lambda */
             /* both searches run against lambda_i > 0: max(-ds/l, -dz/l) = -min(ds, dz)/l */
             tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
@@ -815,7 +848,7 @@ struct Solver {
             d_sz += ds * dz;
             const double k = (ds * dz) * ri;
             B.tb[i] = k;
-            ck[i] = winv * k;
+            P::row_axpy(c, i, winv * k, acc_k);
         }
         if (P::Q > 0) {
             double g[P::QA], dz[P::QA], ds[P::QA], w[P::QA];
@@ -844,7 +877,8 @@ struct Solver {
             for (int i = 1; i < P::Q; ++i) B.kq[i] = B.irho * (c1 * B.lam[i]) + c2 * w[i];
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.kq, B.ieta, qk);
         }
-        rows_t<P>(p, c, col_e, ck, qk, vk);
+        P::soc_apply_t(c, qk, acc_k);
+        p.template from_local_add<N>(acc_k, col_e, vk);
     }
 
     /* ---- pass C: corrector direction of one block (stored as ds~ in ta/tq, dz~ in tb/kq) and its
@@ -853,8 +887,9 @@ struct Solver {
     DCOL_HD static void pass_c(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
                                double sigmu, double (&tm)[2])
     {
-        double ro[P::NOA], rq[P::QA];
-        rows<P, false>(p, c, col_e, dx, ro, rq);
+        double xh[P::NL], rq[P::QA];
+        p.template to_local<N, false>(dx, col_e, xh);
+        P::soc_apply(c, xh, rq);
         const int no = P::n_ort(c);
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
@@ -864,7 +899,7 @@ struct Solver {
             const double lam = (B.so[i] * B.zo[i]) * ri;
             const double d = -lam - B.tb[i] + sigmu * ri; /* lambda^-1 o ds */
             const double bt = -B.ta[i] - d;               /* b~ = -rho~ - d  */
-            const double dz = winv * ro[i] - bt;
+            const double dz = winv * P::row_dot(c, i, xh) - bt;
             const double ds = d - dz;
             tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
             B.ta[i] = ds;
