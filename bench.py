@@ -33,10 +33,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "proximity solves+grads/sec"
 UNIT = "pairs/s"
-WORKLOAD = "config4: synthetic batched proximity sweep, 40 ordered type pairs x random poses, alpha + contact + grad[12]"
+WORKLOAD = ("config4: synthetic batched proximity sweep, 40 ordered type pairs x random poses, alpha + d alpha/d pose [12] "
+            "(what proximity_gradient returns) + iters + status per pair")
 
 
-WORKLOAD5 = "config5: scaled quadrotor hallway, sphere victim vs 1024 obstacles (11 shapes) x 100 knots x candidates, alpha + contact + grad[12]"
+WORKLOAD5 = "config5: scaled quadrotor hallway, sphere victim vs 1024 obstacles (11 shapes) x 100 knots x candidates, alpha + d alpha/d pose [12] + iters + status per pair"
 
 
 def make_batch(n_pairs, seed, workload="config4"):
@@ -221,14 +222,13 @@ def main():
     n_launches = sum(p.n_launches for p in plans)
     pipe = None
     if mode == "fused":
-        contact = torch.empty((B, 3), dtype=torch.float64, device=dev)
         plan_perm = plans[0].perm()
 
         def step():
-            eng.solve_records(plans[0], d1, d2, peer.dest_ptrs, contact=contact)
+            eng.solve_records(plans[0], d1, d2, peer.dest_ptrs)
             peer.handshake()
     else:
-        pipe = parallel.GatherPipeline(bounds, world if mode == "nccl" else 1, dev, with_contact=True)
+        pipe = parallel.GatherPipeline(bounds, world if mode == "nccl" else 1, dev, with_contact=False)
 
         def launch(c, out):
             lo, hi = bounds[c]
@@ -282,7 +282,7 @@ def main():
     flops = flop_model_total(rec, i1, i2, iters)
     kernel_ms = float(kms)
     achieved = flops / (kernel_ms * 1e-3)
-    bytes_alg = B * (96 + 4 + 136)   # poses + perm in, record out
+    bytes_alg = B * (96 + 4 + 112)   # poses + perm in, alpha + grad + iters + status out
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,7 +297,7 @@ def main():
         hi1, hi2 = d.pinned_empty(Be, np.int32), d.pinned_empty(Be, np.int32)
         hp1, hp2 = d.pinned_empty((Be, 6)), d.pinned_empty((Be, 6))
         hi1[:], hi2[:], hp1[:], hp2[:] = i1, i2, p1, p2
-        hout = d.BatchResult(alpha=d.pinned_empty(Be), contact=d.pinned_empty((Be, 3)), grad=d.pinned_empty((Be, 12)),
+        hout = d.BatchResult(alpha=d.pinned_empty(Be), contact=None, grad=d.pinned_empty((Be, 12)),
                              iters=d.pinned_empty(Be, np.int32), status=d.pinned_empty(Be, np.int32))
         for _ in range(2):
             eng.solve_host(hi1, hi2, hp1, hp2, out=hout)
@@ -312,7 +312,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert np.array_equal(hout.iters, iters)
         e2e = {"value": Be * world / float(dt), "unit": UNIT, "h2d_bytes_per_step": Be * (48 + 48 + 4 + 4),
-               "d2h_bytes_per_step": Be * (8 + 24 + 96 + 4 + 4), "ms_per_step": float(dt) * 1e3,
+               "d2h_bytes_per_step": Be * (8 + 96 + 4 + 4), "ms_per_step": float(dt) * 1e3,
                "api": "dcol_proximity_batch_host (ProximityEngine.solve_host), page-locked NumPy buffers, "
                       "includes the per-chunk plan (counting sort)"}
 
@@ -339,13 +339,13 @@ def main():
                          "frac": achieved / fp64_peak,
                          "traffic": {"dram_bytes_per_launch": 143.6e6, "pairs_per_launch": 209715,
                                      "source": "profiles/r01_ncu_full_14kernels.md (ncu --set full, mean of 14 specialisations "
-                                               "at this size; algorithmic 236 B/pair = 49.5e6 B per launch)"},
+                                               "at this size, captured with the contact point also written; algorithmic 212 B/pair = 44.5e6 B per launch)"},
                          "kernel": f"dcol::pair_kernel<P1,P2> ({plans[0].n_groups} specialisations, {n_launches} launches per step)",
                          "kernel_ms_per_step": kernel_ms, "model_flops_per_pair": flops / B,
                          "peak_source": "dcol_measure_fp64_peak in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm": {"achieved": bytes_alg / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_alg / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                                 "bytes_per_pair": 236}},
+                                 "bytes_per_pair": 212}},
         }
         if world == 1 and not args.no_altro:
             # BASELINE.json metric, second half: "ALTRO solve time" of the reference's three scenarios through the
