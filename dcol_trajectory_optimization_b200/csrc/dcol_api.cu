@@ -110,6 +110,9 @@ struct dcol_plan {
     int64_t B, capacity;
     int32_t* d_perm;   /* [capacity] plan order -> pair index             */
     int32_t* d_counts; /* [n_shapes^2 + 1] histogram / cursor + error flag */
+    int32_t* h_mapped; /* page-locked, device-mapped copy of the histogram: read back by a kernel's stores, so the
+                          read-back never queues behind bulk copies on a copy engine */
+    int32_t* d_mapped;
     std::vector<int32_t> h_counts;
     std::vector<Group> groups;
     int32_t n_launches;
@@ -189,6 +192,12 @@ __global__ void plan_scatter(const int32_t* __restrict__ idx1, const int32_t* __
         const int32_t pos = priv ? base_of[key] + atomicAdd(&local[key], 1) : atomicAdd(&cursor[key], 1);
         perm[pos] = (int32_t)k;
     }
+}
+
+__global__ void plan_export_counts(const int32_t* __restrict__ counts, int32_t* __restrict__ mapped, int32_t n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mapped[i] = counts[i];
+    __threadfence_system();
 }
 
 /* pairs the reference cannot assemble (combine_problem_matrices.py:58-67 raises ValueError) */
@@ -355,8 +364,10 @@ static int plan_build(dcol_plan* P, const int32_t* d_idx1, const int32_t* d_idx2
     DCOL_CUDA(cudaMemsetAsync(P->d_counts, 0, sizeof(int32_t) * ((size_t)nk + 1), stream));
     plan_histogram<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, P->d_counts, P->d_counts + nk);
     DCOL_CUDA(cudaGetLastError());
-    DCOL_CUDA(cudaMemcpyAsync(P->h_counts.data(), P->d_counts, sizeof(int32_t) * ((size_t)nk + 1), cudaMemcpyDeviceToHost, stream));
+    plan_export_counts<<<(nk + 1 + 255) / 256 > 64 ? 64 : (nk + 1 + 255) / 256, 256, 0, stream>>>(P->d_counts, P->d_mapped, nk + 1);
+    DCOL_CUDA(cudaGetLastError());
     DCOL_CUDA(cudaStreamSynchronize(stream));
+    memcpy(P->h_counts.data(), P->h_mapped, sizeof(int32_t) * ((size_t)nk + 1));
     if (P->h_counts[nk] != 0) return fail(DCOL_E_INDEX, "shape index out of range");
     int64_t off = 0;
     for (int32_t key = 0; key < nk; ++key) {
@@ -373,8 +384,10 @@ static int plan_build(dcol_plan* P, const int32_t* d_idx1, const int32_t* d_idx2
         off += cnt;
     }
     P->n_launches = (int32_t)P->groups.size();
-    /* h_counts lives in the plan, so the (pageable, staged) copy may complete after we return */
-    DCOL_CUDA(cudaMemcpyAsync(P->d_counts, P->h_counts.data(), sizeof(int32_t) * (size_t)nk, cudaMemcpyHostToDevice, stream));
+    /* cursors go back the same way: written into the mapped buffer, fetched by a kernel (no copy engine) */
+    memcpy(P->h_mapped, P->h_counts.data(), sizeof(int32_t) * (size_t)nk);
+    plan_export_counts<<<(nk + 255) / 256 > 64 ? 64 : (nk + 255) / 256, 256, 0, stream>>>(P->d_mapped, P->d_counts, nk);
+    DCOL_CUDA(cudaGetLastError());
     plan_scatter<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, P->d_counts, P->d_perm);
     DCOL_CUDA(cudaGetLastError());
     return 0;
@@ -389,11 +402,16 @@ static int plan_alloc(const dcol_shape_table* T, int64_t capacity, dcol_plan** o
     P->capacity = capacity;
     P->d_perm = nullptr;
     P->d_counts = nullptr;
+    P->h_mapped = nullptr;
+    P->d_mapped = nullptr;
     P->n_launches = 0;
     cudaError_t e = cudaMalloc(&P->d_counts, sizeof(int32_t) * ((size_t)ns * ns + 1));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&P->h_mapped, sizeof(int32_t) * ((size_t)ns * ns + 1), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&P->d_mapped, P->h_mapped, 0);
     if (e == cudaSuccess && capacity > 0) e = cudaMalloc(&P->d_perm, sizeof(int32_t) * (size_t)capacity);
     if (e != cudaSuccess) {
         cudaFree(P->d_counts);
+        if (P->h_mapped) cudaFreeHost(P->h_mapped);
         delete P;
         return fail_cuda(e, "plan allocation");
     }
@@ -425,6 +443,7 @@ void dcol_plan_destroy(dcol_plan* P)
     DeviceGuard guard_(P->table->device);
     cudaFree(P->d_perm);
     cudaFree(P->d_counts);
+    if (P->h_mapped) cudaFreeHost(P->h_mapped);
     delete P;
 }
 int64_t dcol_plan_size(const dcol_plan* P) { return P ? P->B : 0; }
@@ -541,7 +560,7 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
         if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
     }
-    int64_t kChunk = 1 << 19; /* measured on B200 + PCIe 5: 2^19 pairs (50 MB in, 75 MB out) gives the best overlap */
+    int64_t kChunk = 1 << 20; /* measured on B200 + PCIe 5 (chunks of 2^18..2^22): 2^20 pairs gives the best overlap */
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
     for (int i = 0; i < 2; ++i) {
