@@ -313,3 +313,52 @@ def test_proximity_batch_convenience_and_pinned_buffers(dcol):
     buf[:] = 1.5
     assert buf.shape == (1000, 6) and buf.dtype == np.float64 and float(buf.sum()) == 9000.0
     dcol.pinned_free(buf)
+
+
+def test_abi_argument_errors_and_concurrent_callers(dcol):
+    """Argument errors come back as negative codes with a message (never a crash); two host threads may use
+    one engine at the same time (calls on a table are serialised internally) and get bit-identical results."""
+    import ctypes as C
+    import threading
+    import torch
+    from dcol_trajectory_optimization_b200 import _lib, workloads as W
+    L = _lib.lib()
+    shapes, i1, i2, p1, p2 = W.config4_batch(20_000, seed=21)
+    eng = dcol.ProximityEngine(shapes)
+    plan = eng.plan(i1, i2)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    out = eng.solve(plan, d1, d2)
+    nul = None
+    # null buffers, bad max_iter, unknown flag, bad destination alignment
+    assert L.dcol_proximity_batch_device(plan._handle, nul, d2.data_ptr(), 1e-6, 50, 3, out.alpha.data_ptr(), out.contact.data_ptr(),
+                                         out.grad.data_ptr(), out.iters.data_ptr(), out.status.data_ptr(), None) == -1
+    assert b"null buffer" in L.dcol_last_error()
+    assert L.dcol_proximity_batch_device(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 51, 3, out.alpha.data_ptr(),
+                                         out.contact.data_ptr(), out.grad.data_ptr(), out.iters.data_ptr(), out.status.data_ptr(), None) == -1
+    assert L.dcol_proximity_batch_device(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 50, 64, out.alpha.data_ptr(),
+                                         out.contact.data_ptr(), out.grad.data_ptr(), out.iters.data_ptr(), out.status.data_ptr(), None) == -1
+    arr = (C.c_void_p * 1)(out.grad.data_ptr() + 8)
+    assert L.dcol_proximity_batch_records(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 50, 0, 1, arr, 0, None, None) == -1
+    assert b"16-byte" in L.dcol_last_error()
+    handle = C.c_void_p()
+    rec = eng.records.copy()
+    rec["type"][0] = 99
+    assert L.dcol_shape_table_create(rec.ctypes.data, len(rec), eng.A.ctypes.data, eng.b.ctypes.data, len(eng.b), 0, C.byref(handle)) == -2
+    assert L.dcol_shape_table_create(eng.records.ctypes.data, len(rec), eng.A.ctypes.data, eng.b.ctypes.data, len(eng.b), 99,
+                                     C.byref(handle)) == -1
+    torch.cuda.synchronize()
+    ref = eng.solve_host(i1, i2, p1, p2)
+    results = [None, None]
+
+    def worker(j):
+        for _ in range(5):
+            results[j] = eng.solve_host(i1, i2, p1, p2)
+
+    th = [threading.Thread(target=worker, args=(j,)) for j in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for r in results:
+        assert np.array_equal(r.alpha, ref.alpha) and np.array_equal(r.grad, ref.grad) and np.array_equal(r.iters, ref.iters)
+    assert torch.cuda.current_device() == 0
+    plan.close()
+    eng.close()
