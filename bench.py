@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=1 << 23, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how records reach all ranks")
+    ap.add_argument("--fabric", default="auto", choices=["auto", "multicast", "unicast"], help="--gather fused: NVLS multicast or peer stores")
     ap.add_argument("--chunks", type=int, default=1, help="--gather nccl: chunks per step (gather/solve overlap)")
     ap.add_argument("--ref-pairs", type=int, default=1 << 21, help="pairs per step of the reference arm")
     ap.add_argument("--workload", default="config4", choices=["config4", "config5"])
@@ -205,17 +206,32 @@ def main():
     # the same stream is the completion handshake.  --gather nccl: solve, then all_gather_into_tensor.
     mode = "none" if world == 1 else args.gather
     peer = None
-    if mode == "fused":
-        try:
-            peer = parallel.PeerRecordGather(B, rank, world, local_rank)
-        except Exception as exc:            # no CUDA IPC between the ranks on this box
-            if rank == 0:
-                print(f"# fused gather unavailable ({exc}); using NCCL all-gather", file=sys.stderr, flush=True)
-            mode = "nccl"
-        flag = torch.tensor([1.0 if mode == "fused" else 0.0], device=dev)
+    def agree(ok):      # every rank must take the same path
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if float(flag) == 0.0:
-            mode = "nccl"
+        return float(flag) == 1.0
+
+    if mode == "fused":
+        # 1st choice: NVLink multicast (one multimem.st per 16 B reaches every rank); 2nd: unicast peer stores through
+        # CUDA-IPC mappings; last: solve, then NCCL all-gather
+        if args.fabric in ("auto", "multicast"):
+            try:
+                peer = parallel.MulticastRecordGather(B, rank, world, local_rank)
+            except Exception as exc:
+                peer = None
+                if rank == 0:
+                    print(f"# multicast gather unavailable ({exc})", file=sys.stderr, flush=True)
+            if not agree(peer is not None):
+                peer = None
+        if peer is None:
+            try:
+                peer = parallel.PeerRecordGather(B, rank, world, local_rank)
+            except Exception as exc:            # no CUDA IPC between the ranks on this box
+                peer = None
+                if rank == 0:
+                    print(f"# peer-store gather unavailable ({exc}); using NCCL all-gather", file=sys.stderr, flush=True)
+            if not agree(peer is not None):
+                peer, mode = None, "nccl"
     n_chunks = args.chunks if mode == "nccl" else 1
     bounds = [parallel.shard_bounds(B, c, n_chunks) for c in range(n_chunks)]
     plans = [eng.plan(i1[lo:hi], i2[lo:hi]) for lo, hi in bounds]
@@ -225,7 +241,7 @@ def main():
         plan_perm = plans[0].perm()
 
         def step():
-            eng.solve_records(plans[0], d1, d2, peer.dest_ptrs)
+            eng.solve_records(plans[0], d1, d2, peer.dest_ptrs, multicast=peer.multicast)
             peer.handshake()
     else:
         pipe = parallel.GatherPipeline(bounds, world if mode == "nccl" else 1, dev, with_contact=False)
@@ -328,8 +344,10 @@ def main():
                                "re-evaluates a fixed pair list; the e2e figure re-plans every chunk",
                        "collective": {"none": "none",
                                       "fused": "all-gather fused into the solve: the kernel epilogue stores each 112 B record "
-                                               "(alpha, grad[12], iters, status) to every rank's buffer over NVLink peer "
-                                               "mappings; 4-byte NCCL all-reduce as completion handshake",
+                                               "(alpha, grad[12], iters, status) to every rank's buffer over NVLink ("
+                                               + ("one multimem.st per 16 B through the NVSwitch multicast address"
+                                                  if (peer is not None and peer.multicast) else "unicast stores to CUDA-IPC peer mappings")
+                                               + "); 4-byte NCCL all-reduce as completion handshake",
                                       "nccl": f"all_gather_into_tensor of the 112 B/pair records, {n_chunks} chunk(s) per step"}[mode],
                        "parallelism": f"batch sharded over {world} GPU(s), one process per GPU"},
             "clocks": clocks,

@@ -210,10 +210,14 @@ __global__ void fill_unsupported(BatchArgs b)
     if (b.flags & DCOL_WANT_CONTACT)
         for (int j = 0; j < 3; ++j) b.contact[3 * k + j] = nan;
     if (b.n_dest > 0) {
+        const double last = __longlong_as_double((long long)DCOL_STATUS_UNSUPPORTED << 32);
         for (int d = 0; d < b.n_dest; ++d) {
             double* r = b.dest[d] + kRecordWords * (b.record_offset + b.first + t);
-            for (int j = 0; j < 13; ++j) r[j] = nan;
-            r[13] = __longlong_as_double((long long)DCOL_STATUS_UNSUPPORTED << 32);
+            for (int j = 0; j < kRecordWords; ++j) {
+                const double v = j < 13 ? nan : last;
+                if (b.flags & DCOL_DEST_MULTICAST) asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(r + j), "d"(v) : "memory");
+                else r[j] = v;
+            }
         }
         return;
     }
@@ -473,7 +477,8 @@ int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, cons
                                  int32_t max_iter, uint32_t flags, int32_t n_dest, double* const* dest,
                                  int64_t record_offset, double* d_contact, void* stream_)
 {
-    if (flags & ~(uint32_t)DCOL_FIX_CASE4) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~(uint32_t)(DCOL_FIX_CASE4 | DCOL_DEST_MULTICAST)) return fail(DCOL_E_ARG, "unknown flag");
+    if ((flags & DCOL_DEST_MULTICAST) && n_dest != 1) return fail(DCOL_E_ARG, "a multicast destination must be the only one");
     if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_records: null plan");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
     if (n_dest < 1 || n_dest > DCOL_MAX_DEST || !dest || record_offset < 0) return fail(DCOL_E_ARG, "bad destination list");

@@ -141,9 +141,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid
         const int n_chunks = n_lanes * (kRecordWords / 2);
         const double2* src = reinterpret_cast<const double2*>(stage_w);
         const int64_t t0 = t - lane; /* first pair of this warp */
-        for (int d = 0; d < a.b.n_dest; ++d) {
-            double2* dst = reinterpret_cast<double2*>(a.b.dest[d] + kRecordWords * (a.b.record_offset + a.b.first + t0));
-            for (int c = lane; c < n_chunks; c += n_lanes) dst[c] = src[c];
+        if (a.b.flags & DCOL_DEST_MULTICAST) {
+            /* dest[0] is a multicast address: ONE multimem store per 16 bytes, replicated by the NVSwitch into the
+             * same offset of every rank's buffer (NVLink SHARP) — the all-gather costs this GPU 112 B/pair of egress
+             * instead of 112 B x (world - 1) */
+            const float4* src4 = reinterpret_cast<const float4*>(stage_w);
+            float4* dst = reinterpret_cast<float4*>(a.b.dest[0] + kRecordWords * (a.b.record_offset + a.b.first + t0));
+            for (int c = lane; c < n_chunks; c += n_lanes) {
+                const float4 v = src4[c];
+                asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x), "f"(v.y),
+                             "f"(v.z), "f"(v.w)
+                             : "memory");
+            }
+            /* no fence here: the grid's completion makes the stores visible, and the caller's handshake orders
+             * it before any consumer */
+        } else {
+            for (int d = 0; d < a.b.n_dest; ++d) {
+                double2* dst = reinterpret_cast<double2*>(a.b.dest[d] + kRecordWords * (a.b.record_offset + a.b.first + t0));
+                for (int c = lane; c < n_chunks; c += n_lanes) dst[c] = src[c];
+            }
         }
     }
     if (a.b.trace) {

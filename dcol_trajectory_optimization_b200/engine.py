@@ -190,7 +190,7 @@ class ProximityEngine:
         return out
 
     def solve_records(self, plan: Plan, pose1, pose2, dest_ptrs, record_offset: int = 0, tol: float = 1e-6,
-                      max_iter: int = 50, contact=None, fix_case4: bool = False):
+                      max_iter: int = 50, contact=None, fix_case4: bool = False, multicast: bool = False):
         """Record mode: every pair's 112-byte record ``{alpha, grad[12], iters, status}`` is written, in plan
         order, to each of the raw device addresses ``dest_ptrs`` (local buffers or peer-GPU buffers mapped with
         CUDA IPC — the all-gather of the results fused into the solve).  Enqueues on the current stream."""
@@ -203,7 +203,7 @@ class ProximityEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().dcol_proximity_batch_records(
             plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter),
-            FIX_CASE4 if fix_case4 else 0, len(dest_ptrs), arr,
+            (FIX_CASE4 if fix_case4 else 0) | (_lib.DEST_MULTICAST if multicast else 0), len(dest_ptrs), arr,
             int(record_offset), contact.data_ptr() if contact is not None else None, stream))
 
     # ------------------------------------------------------------------ host buffers

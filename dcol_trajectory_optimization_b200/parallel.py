@@ -144,6 +144,8 @@ class PeerRecordGather:
     ``engine.records_to_result(gathered[r], perm_r)`` for pair order).  All ranks must use the same ``B``.
     """
 
+    multicast = False
+
     def __init__(self, B: int, rank: int, world: int, local_device: int, group=None):
         import ctypes as C
         import torch.distributed as dist
@@ -192,3 +194,38 @@ class PeerRecordGather:
         if self._ptr:
             L.dcol_device_free(self.dev, self._ptr)
             self._ptr = None
+
+
+class MulticastRecordGather:
+    """The fused all-gather over NVLink SHARP: the gathered buffers of all ranks are one symmetric allocation
+    (``torch.distributed._symmetric_memory``) with a MULTICAST address, and the solve kernel's epilogue issues one
+    ``multimem.st`` per 16 bytes of a record; the NVSwitch replicates it into slot ``rank`` of every rank's
+    buffer.  Egress per GPU is 112 B/pair, independent of the world size.  Same interface as
+    :class:`PeerRecordGather`; raises if the fabric has no multicast support (callers then fall back to it)."""
+
+    multicast = True
+
+    def __init__(self, B: int, rank: int, world: int, local_device: int, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.B, self.rank, self.world, self.dev, self.group = B, rank, world, local_device, group
+        dev = torch.device("cuda", local_device)
+        flat = symm_mem.empty(world * max(B, 1) * _lib.RECORD_WORDS, dtype=torch.float64, device=dev)
+        self._hdl = symm_mem.rendezvous(flat, group if group is not None else dist.group.WORLD)
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("symmetric memory has no multicast address on this fabric")
+        self._flat = flat
+        self.gathered = flat.view(world, max(B, 1), _lib.RECORD_WORDS)[:, :B]
+        self.dest_ptrs = [mc + B * _lib.RECORD_WORDS * 8 * rank]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def handshake(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        self._hdl = None
+        self._flat = None

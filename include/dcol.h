@@ -76,6 +76,8 @@ enum {
 enum {
     DCOL_WANT_CONTACT = 1u, /* x[0:3] of the solution, proximity.py:52                        */
     DCOL_WANT_GRAD    = 2u, /* d alpha / d [r1 p1 r2 p2], proximity_gradient.py:71-77 layout  */
+    DCOL_DEST_MULTICAST = 8u, /* dcol_proximity_batch_records only: dest[0] is an NVLink multicast address (NVLS);
+                                 every record leaves as multimem.st and the switch delivers it to all ranks' buffers */
     DCOL_FIX_CASE4    = 4u  /* EXTENSION: also solve the pairs in which both primitives carry extra variables
                                (capsule / cylinder / polygon squared), with the column layout
                                [x, alpha, extras1, extras2] that combine_problem_matrices.py:58-67 builds for the
@@ -142,7 +144,7 @@ int dcol_proximity_batch_device(const dcol_plan* plan, const double* d_pose1, co
 #define DCOL_MAX_DEST 8
 #define DCOL_RECORD_WORDS 14
 int dcol_proximity_batch_records(const dcol_plan* plan, const double* d_pose1, const double* d_pose2, double tol,
-                                 int32_t max_iter, uint32_t flags /* DCOL_FIX_CASE4 or 0 */, int32_t n_dest,
+                                 int32_t max_iter, uint32_t flags /* DCOL_FIX_CASE4 | DCOL_DEST_MULTICAST */, int32_t n_dest,
                                  double* const* dest, int64_t record_offset, double* d_contact, void* stream);
 /* Device pointer to the plan's permutation: perm[i] = index (in the caller's arrays) of the i-th pair in
  * plan order; valid until dcol_plan_destroy. */

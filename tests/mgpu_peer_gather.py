@@ -25,11 +25,21 @@ def main():
     eng = d.ProximityEngine(shapes, device=local)
     plan = eng.plan(i1, i2)
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
-    pg = parallel.PeerRecordGather(B, rank, world, local)
+    fabric = sys.argv[1] if len(sys.argv) > 1 else "unicast"
+    if fabric == "multicast":
+        try:
+            pg = parallel.MulticastRecordGather(B, rank, world, local)
+        except Exception as exc:
+            print("MULTICAST_UNAVAILABLE", rank, repr(exc)[:200], flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            return
+    else:
+        pg = parallel.PeerRecordGather(B, rank, world, local)
     pg.gathered.fill_(-1.0)
     dist.barrier()
     torch.cuda.synchronize()
-    eng.solve_records(plan, d1, d2, pg.dest_ptrs)
+    eng.solve_records(plan, d1, d2, pg.dest_ptrs, multicast=pg.multicast)
     pg.handshake()
     torch.cuda.synchronize()
     # every rank's perm differs: exchange them once (static per plan)

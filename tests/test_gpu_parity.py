@@ -281,9 +281,11 @@ def test_record_mode_matches_array_mode(dcol):
     eng.close()
 
 
-def test_peer_record_gather_two_gpus():
-    """The fused all-gather on 2 GPUs (one process per GPU, CUDA IPC peer mappings): every rank ends up
-    with every rank's records.  Skipped on a single-GPU box."""
+@pytest.mark.parametrize("fabric", ["unicast", "multicast"])
+def test_peer_record_gather_two_gpus(fabric):
+    """The fused all-gather on 2 GPUs (one process per GPU): unicast stores through CUDA IPC peer mappings, and
+    multimem stores through the NVSwitch multicast address of a symmetric allocation; every rank ends up with
+    every rank's records.  Skipped on a single-GPU box (and, for multicast, on a fabric without NVLS)."""
     import os
     import subprocess
     import sys
@@ -293,8 +295,10 @@ def test_peer_record_gather_two_gpus():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
-                        os.path.join(root, "tests", "mgpu_peer_gather.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(root, "tests", "mgpu_peer_gather.py"), fabric], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    if "MULTICAST_UNAVAILABLE" in r.stdout:
+        pytest.skip("no NVLink multicast on this box: " + r.stdout[-300:])
     assert r.stdout.count("PEER_GATHER_OK") == 2
 
 
