@@ -366,3 +366,36 @@ def test_abi_argument_errors_and_concurrent_callers(dcol):
     assert torch.cuda.current_device() == 0
     plan.close()
     eng.close()
+
+
+def test_many_distinct_shapes_global_histogram_path(dcol, oracle):
+    """80 distinct shapes -> 6,400 (shape, shape) keys: the plan's counting sort leaves its shared-memory path
+    (<= 4,096 keys) for global atomics, and a solve has thousands of small groups."""
+    from dcol_trajectory_optimization_b200.shapes import flatten_shapes
+    rng = np.random.default_rng(3)
+    shapes = []
+    for j in range(80):
+        kind = j % 4
+        if kind == 0:
+            shapes.append(dcol.create_rect_prism(*rng.uniform(0.5, 3.0, size=3)))
+        elif kind == 1:
+            shapes.append(dcol.SphereMRP(rng.uniform(0.2, 1.0)))
+        elif kind == 2:
+            shapes.append(dcol.ConeMRP(rng.uniform(1.0, 3.0), np.deg2rad(rng.uniform(15, 30))))
+        else:
+            shapes.append(dcol.CapsuleMRP(rng.uniform(0.2, 0.6), rng.uniform(0.5, 2.0)))
+    rec, A, b = flatten_shapes(shapes)
+    n = 30_000
+    i1 = rng.integers(0, 80, size=n).astype(np.int32)
+    i2 = rng.integers(0, 80, size=n).astype(np.int32)
+    from dcol_trajectory_optimization_b200 import workloads as W
+    p1, p2 = W.config4_poses(n, seed=17)
+    ref = oracle.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=oracle.GRAD_EXACT)
+    eng = dcol.ProximityEngine((rec, A, b))
+    res = eng.solve_host(i1, i2, p1, p2)
+    eng.close()
+    assert np.array_equal(res.status, ref["status"]) and np.array_equal(res.iters, ref["iters"])
+    assert set(np.unique(ref["status"])) == {0, 4}          # capsule x capsule pairs are unsupported in parity mode
+    ok = ref["status"] == 0
+    assert _alpha_err(res.alpha[ok], ref["alpha"][ok]).max() < ALPHA_RTOL
+    assert np.quantile(_grad_err(res.grad[ok], ref["grad"][ok]), 0.9999) < GRAD_RTOL
