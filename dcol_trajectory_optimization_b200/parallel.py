@@ -229,3 +229,77 @@ class MulticastRecordGather:
     def close(self):
         self._hdl = None
         self._flat = None
+
+
+class FusedShardedSolver:
+    """Multi-GPU entry point: every rank passes the SAME global batch description, solves its contiguous shard and
+    ends up with the results of ALL pairs (pair order), the all-gather being fused into the solve kernel.
+
+    Set up once per (engine, idx1, idx2): shard bounds, the local plan, the gathered buffers (NVLink multicast if the
+    fabric has it, else unicast CUDA-IPC peer stores) and every rank's plan permutation (exchanged once, it is static).
+    ``solve(pose1, pose2)`` then takes the global ``[B, 6]`` pose tensors (CUDA, this rank's device; only the local
+    shard is read) and returns a :class:`BatchResult` over all ``B`` pairs."""
+
+    def __init__(self, engine, idx1, idx2, rank: int, world: int, group=None, fabric: str = "auto"):
+        import torch.distributed as dist
+        self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        idx1, idx2 = torch.as_tensor(idx1), torch.as_tensor(idx2)
+        self.B = int(idx1.shape[0])
+        self.bounds = [shard_bounds(self.B, r, world) for r in range(world)]
+        self.Bmax = max(hi - lo for lo, hi in self.bounds)
+        lo, hi = self.bounds[rank]
+        self.lo, self.n = lo, hi - lo
+        # every rank's shard is padded to Bmax pairs by repeating its last pair, so that all slots have one size
+        sel = torch.arange(lo, lo + self.Bmax).clamp(max=max(hi - 1, lo))
+        self._sel = sel.to(engine.device)
+        self.plan = engine.plan(idx1[sel], idx2[sel])
+        dev = engine.device.index
+        self.gather = None
+        if world > 1:
+            def agree(ok):
+                flag = torch.tensor([1.0 if ok else 0.0], device=engine.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                return float(flag) == 1.0
+            if fabric in ("auto", "multicast"):
+                try:
+                    self.gather = MulticastRecordGather(self.Bmax, rank, world, dev, group)
+                except Exception:
+                    self.gather = None
+                if not agree(self.gather is not None):
+                    self.gather = None
+            if self.gather is None:
+                self.gather = PeerRecordGather(self.Bmax, rank, world, dev, group)
+            perms = [torch.empty(self.Bmax, dtype=torch.int32, device=engine.device) for _ in range(world)]
+            dist.all_gather(perms, self.plan.perm(), group=group)
+        else:
+            self._local = torch.empty((1, self.Bmax, WORDS_PER_PAIR), dtype=torch.float64, device=engine.device)
+            perms = [self.plan.perm()]
+        # scatter map: record i of rank r belongs to global pair bounds[r].lo + perm_r[i] (padding rows dropped)
+        dst, src = [], []
+        for r, (rlo, rhi) in enumerate(self.bounds):
+            pr = perms[r].long()
+            keep = pr < (rhi - rlo)
+            dst.append(rlo + pr[keep])
+            src.append(r * self.Bmax + torch.nonzero(keep).squeeze(1))
+        self._dst, self._src = torch.cat(dst), torch.cat(src)
+
+    def solve(self, pose1, pose2, tol: float = 1e-6, max_iter: int = 50) -> BatchResult:
+        from .engine import records_to_result
+        p1 = pose1.index_select(0, self._sel).contiguous()
+        p2 = pose2.index_select(0, self._sel).contiguous()
+        if self.world > 1:
+            self.engine.solve_records(self.plan, p1, p2, self.gather.dest_ptrs, tol=tol, max_iter=max_iter,
+                                      multicast=self.gather.multicast)
+            self.gather.handshake()
+            rec = self.gather.gathered.reshape(self.world * self.Bmax, WORDS_PER_PAIR)
+        else:
+            self.engine.solve_records(self.plan, p1, p2, [self._local.data_ptr()], tol=tol, max_iter=max_iter)
+            rec = self._local.reshape(self.Bmax, WORDS_PER_PAIR)
+        out = torch.empty((self.B, WORDS_PER_PAIR), dtype=torch.float64, device=rec.device)
+        out[self._dst] = rec[self._src]
+        return records_to_result(out)
+
+    def close(self):
+        if self.gather is not None:
+            self.gather.close()
+        self.plan.close()

@@ -53,6 +53,18 @@ def main():
         torch.cuda.synchronize()
         assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status), f"rank {rank} slot {r}"
         assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad), f"rank {rank} slot {r}"
+    # the user-facing form: same global batch on every rank, results of all pairs everywhere, in pair order
+    from dcol_trajectory_optimization_b200 import workloads as W2
+    shapes_g, g1, g2, q1, q2 = W2.config4_batch(20_003, seed=55)           # odd size: shards of 10,002 / 10,001
+    eng_g = d.ProximityEngine(shapes_g, device=local)
+    fs = parallel.FusedShardedSolver(eng_g, g1, g2, rank, world, fabric=fabric)
+    got = fs.solve(torch.from_numpy(q1).to(dev), torch.from_numpy(q2).to(dev))
+    pl = eng_g.plan(g1, g2)
+    want = eng_g.solve(pl, torch.from_numpy(q1).to(dev), torch.from_numpy(q2).to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status)
+    assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad)
+    fs.close()
     print("PEER_GATHER_OK", rank, flush=True)
     dist.barrier()
     pg.close()

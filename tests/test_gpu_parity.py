@@ -399,3 +399,22 @@ def test_many_distinct_shapes_global_histogram_path(dcol, oracle):
     ok = ref["status"] == 0
     assert _alpha_err(res.alpha[ok], ref["alpha"][ok]).max() < ALPHA_RTOL
     assert np.quantile(_grad_err(res.grad[ok], ref["grad"][ok]), 0.9999) < GRAD_RTOL
+
+
+def test_fused_sharded_solver_single_rank(dcol):
+    """FusedShardedSolver with world = 1 (no fabric): records in plan order scattered back to pair order."""
+    import torch
+    from dcol_trajectory_optimization_b200 import parallel, workloads as W
+    shapes, i1, i2, p1, p2 = W.config4_batch(5_003, seed=8)
+    eng = dcol.ProximityEngine(shapes)
+    fs = parallel.FusedShardedSolver(eng, i1, i2, 0, 1)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    got = fs.solve(d1, d2)
+    plan = eng.plan(i1, i2)
+    want = eng.solve(plan, d1, d2)
+    torch.cuda.synchronize()
+    assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad)
+    assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status)
+    fs.close()
+    plan.close()
+    eng.close()
