@@ -52,6 +52,20 @@ class BatchResult:
     iters: object      # [B]      PDIP iterations taken
     status: object     # [B]      DCOL_STATUS_*
 
+    def summary(self) -> dict:
+        """Per-batch counters (the reference has no logging inside the solver): how many pairs
+        ended in each status and the histogram of PDIP iteration counts of the converged ones."""
+        status = self.status.cpu().numpy() if hasattr(self.status, "cpu") else np.asarray(self.status)
+        iters = self.iters.cpu().numpy() if hasattr(self.iters, "cpu") else np.asarray(self.iters)
+        names = ("ok", "max_iter", "non_finite", "not_pd", "unsupported")
+        counts = np.bincount(status, minlength=5)
+        ok = status == STATUS_OK
+        hist = np.bincount(iters[ok], minlength=1) if ok.any() else np.zeros(1, dtype=np.int64)
+        return {"pairs": int(status.shape[0]), "status": {n: int(c) for n, c in zip(names, counts)},
+                "iters_mean": float(iters[ok].mean()) if ok.any() else float("nan"),
+                "iters_max": int(iters[ok].max()) if ok.any() else 0,
+                "iters_hist": {int(i): int(c) for i, c in enumerate(hist) if c}}
+
 
 class _DevArray:
     """A raw device address exposed through ``__cuda_array_interface__`` so torch can view it."""

@@ -88,3 +88,12 @@ def test_flop_model_examples():
     assert fit(12, 0, 0, 4, 6, 6, True, True) == 1585
     assert fit(7, 3, 0, 4, 0, 6, False, True) == 1851
     assert fit(0, 4, 4, 4, 0, 0, False, False) == 2741
+
+
+def test_batch_result_summary():
+    from dcol_trajectory_optimization_b200 import BatchResult
+    r = BatchResult(alpha=np.zeros(6), contact=None, grad=None, iters=np.array([5, 6, 6, 0, 50, 7], np.int32),
+                    status=np.array([0, 0, 0, 4, 1, 0], np.int32))
+    s = r.summary()
+    assert s["pairs"] == 6 and s["status"] == {"ok": 4, "max_iter": 1, "non_finite": 0, "not_pd": 0, "unsupported": 1}
+    assert s["iters_hist"] == {5: 1, 6: 2, 7: 1} and s["iters_max"] == 7 and abs(s["iters_mean"] - 6.0) < 1e-12
