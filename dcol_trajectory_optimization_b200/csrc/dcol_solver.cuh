@@ -356,9 +356,8 @@ struct Prim {
 
     /* one orthant row: value on a local vector, rank-one Gram update, axpy into a local adjoint accumulator
      * (the passes of the solver fuse these per row so that per-row temporaries die immediately) */
-    DCOL_HD static double row_dot(const Const& c, int i, const double (&xh)[NL])
+    DCOL_HD static double row_dot(const Const& c, int i, const double (&xh)[NL], double t = 0.0)
     {
-        double t = 0.0;
         DCOL_UNROLL
         for (int j = 0; j < NL; ++j)
             if (nz(i, j)) t += g(c, i, j) * xh[j];
@@ -750,7 +749,7 @@ struct Solver {
             if (P::dyn && i >= no) break;
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;                             /* 1 / w_i                       */
-            const double rho = winv * (B.so[i] + P::row_dot(c, i, xh));   /* (W^-1 rz)_i, rz = s + G x - h */
+            const double rho = winv * P::row_dot(c, i, xh, B.so[i]);      /* (W^-1 rz)_i, rz = s + G x - h */
             B.ta[i] = rho;
             P::row_gram_add(c, i, winv * winv, Gl);
             /* -W^-2 rz: b~_affine = lambda - rho~, and G~^T lambda = G^T z cancels in bx */
@@ -826,7 +825,7 @@ struct Solver {
      * the centring ratio, k = lambda^-1 o (ds~ o dz~) and G~^T k */
     template <class P>
     DCOL_HD static void pass_b(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
-                               double (&tm)[2], double& d_l, double& d_sz, double (&vk)[N])
+                               double (&tm)[2], double& d_sz, double (&vk)[N])
     {
         double xh[P::NL], rq[P::QA], acc_k[P::NL], qk[P::QA];
         p.template to_local<N, false>(dx, col_e, xh); /* G dx */
@@ -840,11 +839,11 @@ struct Solver {
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;
             const double lam = (B.so[i] * B.zo[i]) * ri;
-            const double dz = winv * P::row_dot(c, i, xh) - (lam - B.ta[i]); /* dz~ = G~ dx - b~ */
-            const double ds = -lam - dz;                      /* ds~ = d - dz~, d = -lambda */
+            /* ds~ = W^-1 ds with ds = -rz - G dx (primal equation), dz~ = d - ds~ with d = -lambda (complementarity) */
+            const double ds = -fma(winv, P::row_dot(c, i, xh), B.ta[i]);
+            const double dz = -lam - ds;
             /* both searches run against lambda_i > 0: max(-ds/l, -dz/l) = -min(ds, dz)/l */
             tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
-            d_l += lam * (ds + dz);
             d_sz += ds * dz;
             const double k = (ds * dz) * ri;
             B.tb[i] = k;
@@ -857,7 +856,6 @@ struct Solver {
             for (int i = 0; i < P::Q; ++i) {
                 dz[i] = g[i] - (B.lam[i] - B.tq[i]);
                 ds[i] = -B.lam[i] - dz[i];
-                d_l += B.lam[i] * (ds[i] + dz[i]);
                 d_sz += ds[i] * dz[i];
             }
             tm[0] = max_(tm[0], soc_ls<P>(B, ds));
@@ -898,9 +896,8 @@ struct Solver {
             const double winv = B.zo[i] * ri;
             const double lam = (B.so[i] * B.zo[i]) * ri;
             const double d = -lam - B.tb[i] + sigmu * ri; /* lambda^-1 o ds */
-            const double bt = -B.ta[i] - d;               /* b~ = -rho~ - d  */
-            const double dz = winv * P::row_dot(c, i, xh) - bt;
-            const double ds = d - dz;
+            const double ds = -fma(winv, P::row_dot(c, i, xh), B.ta[i]); /* -rho~ - G~ dx (primal equation) */
+            const double dz = d - ds;
             tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
             B.ta[i] = ds;
             B.tb[i] = dz;
@@ -1088,14 +1085,15 @@ struct Solver {
             chol_solve(L, Li, dx);
 
             /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
-            double tm[2] = { 0.0, 0.0 }, d_l = 0.0, d_sz = 0.0, vk[N];
+            double tm[2] = { 0.0, 0.0 }, d_sz = 0.0, vk[N];
             DCOL_UNROLL
             for (int j = 0; j < N; ++j) vk[j] = 0.0;
-            pass_b<F1>(p1, c1, CE1, b1, dx, tm, d_l, d_sz, vk);
-            pass_b<F2>(p2, c2, CE2, b2, dx, tm, d_l, d_sz, vk);
+            pass_b<F1>(p1, c1, CE1, b1, dx, tm, d_sz, vk);
+            pass_b<F2>(p2, c2, CE2, b2, dx, tm, d_sz, vk);
             double t = max_(tm[0], tm[1]);
             double a = t > 1.0 ? rcp_(t) : 1.0;
-            const double rho = (sz + a * d_l + (a * a) * d_sz) * rcp_(sz);
+            /* (s + a ds)'(z + a dz) / s'z with ds~ + dz~ = -lambda for the affine direction: 1 - a + a^2 <ds~, dz~> / s'z */
+            const double rho = (1.0 - a) + (a * a) * (d_sz * rcp_(sz));
             const double cl = max_(0.0, min_(1.0, rho));
             const double sigmu = (cl * cl * cl) * mu;
 
