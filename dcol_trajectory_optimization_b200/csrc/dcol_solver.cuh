@@ -838,7 +838,7 @@ struct Solver {
             if (P::dyn && i >= no) break;
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;
-            const double lam = (B.so[i] * B.zo[i]) * ri;
+            const double lam = B.so[i] * winv; /* lambda_i = s_i / w_i */
             /* ds~ = W^-1 ds with ds = -rz - G dx (primal equation), dz~ = d - ds~ with d = -lambda (complementarity) */
             const double ds = -fma(winv, P::row_dot(c, i, xh), B.ta[i]);
             const double dz = -lam - ds;
@@ -894,7 +894,7 @@ struct Solver {
             if (P::dyn && i >= no) break;
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;
-            const double lam = (B.so[i] * B.zo[i]) * ri;
+            const double lam = B.so[i] * winv; /* lambda_i = s_i / w_i */
             const double d = -lam - B.tb[i] + sigmu * ri; /* lambda^-1 o ds */
             const double ds = -fma(winv, P::row_dot(c, i, xh), B.ta[i]); /* -rho~ - G~ dx (primal equation) */
             const double dz = d - ds;
@@ -931,10 +931,9 @@ struct Solver {
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
-            const double ri = B.rinv[i];
-            const double w = B.so[i] * ri, winv = B.zo[i] * ri;
-            B.so[i] += a * (w * B.ta[i]);
-            B.zo[i] += a * (winv * B.tb[i]);
+            const double ar = a * B.rinv[i]; /* a w_i = s_i (a / lambda_i),  a / w_i = z_i (a / lambda_i) */
+            B.so[i] = fma(B.so[i] * ar, B.ta[i], B.so[i]);
+            B.zo[i] = fma(B.zo[i] * ar, B.tb[i], B.zo[i]);
         }
         if (P::Q > 0) {
             double ds[P::QA], dz[P::QA];
