@@ -374,6 +374,19 @@ struct Prim {
                 if (nz(i, k)) Gl[j][k] += wg * g(c, i, k);
         }
     }
+    /* Gl += w row row^T and acc -= (w r) row in one sweep: the products w g_j are shared */
+    DCOL_HD static void row_gram_axpy(const Const& c, int i, double w, double r, double (&Gl)[NL][NL], double (&acc)[NL])
+    {
+        DCOL_UNROLL
+        for (int j = 0; j < NL; ++j) {
+            if (!nz(i, j)) continue;
+            const double wg = w * g(c, i, j);
+            acc[j] = fma(-wg, r, acc[j]);
+            DCOL_UNROLL
+            for (int k = j; k < NL; ++k)
+                if (nz(i, k)) Gl[j][k] += wg * g(c, i, k);
+        }
+    }
     DCOL_HD static void row_axpy(const Const& c, int i, double cf, double (&acc)[NL])
     {
         DCOL_UNROLL
@@ -749,11 +762,10 @@ struct Solver {
             if (P::dyn && i >= no) break;
             const double ri = B.rinv[i];
             const double winv = B.zo[i] * ri;                             /* 1 / w_i                       */
-            const double rho = winv * P::row_dot(c, i, xh, B.so[i]);      /* (W^-1 rz)_i, rz = s + G x - h */
-            B.ta[i] = rho;
-            P::row_gram_add(c, i, winv * winv, Gl);
-            /* -W^-2 rz: b~_affine = lambda - rho~, and G~^T lambda = G^T z cancels in bx */
-            P::row_axpy(c, i, -(winv * rho), acc_a);
+            const double rz = P::row_dot(c, i, xh, B.so[i]);              /* rz_i = s_i + (G x - h)_i      */
+            B.ta[i] = winv * rz;                                          /* rho~_i = (W^-1 rz)_i          */
+            /* Gram += w^-2 g g^T and acc_a -= w^-2 rz g  (b~_affine = lambda - rho~; G~^T lambda = G^T z cancels in bx) */
+            P::row_gram_axpy(c, i, winv * winv, rz, Gl, acc_a);
             P::row_axpy(c, i, winv * ri, acc_l);                          /* W^-1 (lambda^-1 o e) */
         }
         if (P::Q > 0) {
