@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-altro", action="store_true", help="skip the three ALTRO scenario solves (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-jacobian", action="store_true", help="skip the solution-Jacobian throughput line (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -371,6 +372,23 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from run_altro import run as run_altro
             line["altro"] = run_altro()
+        if world == 1 and not args.no_jacobian:
+            # extension: the same solve plus the solution Jacobian d(contact, alpha)/d pose
+            # [4][12], from the separate jacobian kernels (dcol_proximity_batch_jacobian); not part of `value`
+            nj = min(B, 1 << 21)
+            jplan = eng.plan(i1[:nj], i2[:nj])
+            jout = None
+            jev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for s_ in range(5):
+                if s_ == 2:
+                    jev[0].record()
+                jout = eng.solve(jplan, d1[:nj], d2[:nj], want_contact=False, want_jac=True, out=jout)
+            jev[1].record()
+            torch.cuda.synchronize()
+            jms = jev[0].elapsed_time(jev[1]) / 3
+            line["jacobian"] = {"value": nj / (jms * 1e-3), "unit": UNIT, "pairs_per_step": nj, "ms_per_step": jms,
+                                "finite": bool(torch.isfinite(jout.jac).all()),
+                                "outputs": "alpha + grad[12] + jac[4][12] + iters + status (496 B/pair)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)

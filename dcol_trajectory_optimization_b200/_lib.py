@@ -23,7 +23,8 @@ MAX_DEST, RECORD_WORDS = 8, 14
 SYMBOLS = (
     "dcol_version", "dcol_last_error", "dcol_device_count", "dcol_shape_table_create", "dcol_shape_table_destroy",
     "dcol_plan_create", "dcol_plan_destroy", "dcol_plan_size", "dcol_plan_n_groups", "dcol_plan_n_launches",
-    "dcol_proximity_batch_device", "dcol_proximity_batch_host", "dcol_host_alloc", "dcol_host_free",
+    "dcol_proximity_batch_device", "dcol_proximity_batch_jacobian", "dcol_proximity_batch_host", "dcol_host_alloc",
+    "dcol_host_free",
     "dcol_proximity_batch_records", "dcol_plan_perm", "dcol_device_alloc", "dcol_device_free", "dcol_ipc_export",
     "dcol_ipc_import", "dcol_ipc_close",
     "dcol_debug_trace_pair", "dcol_measure_fp64_peak",
@@ -77,6 +78,8 @@ def lib():
     L.dcol_plan_n_launches.argtypes = [vp]
     L.dcol_proximity_batch_device.restype = C.c_int
     L.dcol_proximity_batch_device.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_uint32, dp, dp, dp, ip, ip, vp]
+    L.dcol_proximity_batch_jacobian.restype = C.c_int
+    L.dcol_proximity_batch_jacobian.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_uint32, dp, dp, dp, dp, ip, ip, vp]
     L.dcol_proximity_batch_host.restype = C.c_int
     L.dcol_proximity_batch_host.argtypes = [vp, ip, ip, dp, dp, C.c_int64, C.c_double, C.c_int32, C.c_uint32,
                                             dp, dp, dp, ip, ip]

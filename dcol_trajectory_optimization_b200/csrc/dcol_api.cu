@@ -221,6 +221,8 @@ __global__ void fill_unsupported(BatchArgs b)
         }
         return;
     }
+    if (b.jac)
+        for (int j = 0; j < 48; ++j) b.jac[48 * k + j] = nan;
     b.status[k] = DCOL_STATUS_UNSUPPORTED;
     b.iters[k] = 0;
     b.alpha[k] = nan;
@@ -248,6 +250,22 @@ cudaError_t launch_group(const dcol_shape_table* T, int32_t i1, int32_t i2, cons
 {
     GroupLaunch g = { &T->shapes[i1], &T->shapes[i2], T->A.data(), T->b.data(), args };
     const int c2 = T->cls[i2];
+    if (args.jac) { /* solution-Jacobian kernels (dcol_jac_*.cu) */
+        switch (T->cls[i1]) {
+        case CLS_POLY6: return launch_first_class_jac<CLS_POLY6>(c2, g, stream);
+        case CLS_POLY8: return launch_first_class_jac<CLS_POLY8>(c2, g, stream);
+        case CLS_POLYN: return launch_first_class_jac<CLS_POLYN>(c2, g, stream);
+        case CLS_CAPSULE: return launch_first_class_jac<CLS_CAPSULE>(c2, g, stream);
+        case CLS_CYLINDER: return launch_first_class_jac<CLS_CYLINDER>(c2, g, stream);
+        case CLS_CONE: return launch_first_class_jac<CLS_CONE>(c2, g, stream);
+        case CLS_SPHERE: return launch_first_class_jac<CLS_SPHERE>(c2, g, stream);
+        case CLS_PGON5: return launch_first_class_jac<CLS_PGON5>(c2, g, stream);
+        case CLS_PGONN: return launch_first_class_jac<CLS_PGONN>(c2, g, stream);
+        case CLS_BOX: return launch_first_class_jac<CLS_BOX>(c2, g, stream);
+        case CLS_ELLIPSOID: return launch_first_class_jac<CLS_ELLIPSOID>(c2, g, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (T->cls[i1]) {
     case CLS_POLY6: return launch_first_class<CLS_POLY6>(c2, g, stream);
     case CLS_POLY8: return launch_first_class<CLS_POLY8>(c2, g, stream);
@@ -456,7 +474,8 @@ int32_t dcol_plan_n_launches(const dcol_plan* P) { return P ? P->n_launches : 0;
 
 static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol, int32_t max_iter,
                       uint32_t flags, double* d_alpha, double* d_contact, double* d_grad, int32_t* d_iters,
-                      int32_t* d_status, int32_t n_dest, double* const* dest, int64_t record_offset, void* stream_);
+                      int32_t* d_status, int32_t n_dest, double* const* dest, int64_t record_offset, void* stream_,
+                      double* d_jac = nullptr);
 
 int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
                                 int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact, double* d_grad,
@@ -471,6 +490,21 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
         return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null buffer");
     return solve_plan(P, d_pose1, d_pose2, tol, max_iter, flags, d_alpha, d_contact, d_grad, d_iters, d_status, 0, nullptr, 0,
                       stream_);
+}
+
+int dcol_proximity_batch_jacobian(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
+                                  int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact, double* d_grad,
+                                  double* d_jac, int32_t* d_iters, int32_t* d_status, void* stream_)
+{
+    if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_jacobian: null plan");
+    if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
+    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4)) return fail(DCOL_E_ARG, "unknown flag");
+    if (P->B == 0) return 0;
+    if (!d_pose1 || !d_pose2 || !d_alpha || !d_jac || !d_iters || !d_status || ((flags & DCOL_WANT_CONTACT) && !d_contact) ||
+        ((flags & DCOL_WANT_GRAD) && !d_grad))
+        return fail(DCOL_E_ARG, "dcol_proximity_batch_jacobian: null buffer");
+    return solve_plan(P, d_pose1, d_pose2, tol, max_iter, flags, d_alpha, d_contact, d_grad, d_iters, d_status, 0, nullptr, 0,
+                      stream_, d_jac);
 }
 
 int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol,
@@ -494,7 +528,8 @@ const int32_t* dcol_plan_perm(const dcol_plan* P) { return P ? P->d_perm : nullp
 
 static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol, int32_t max_iter,
                       uint32_t flags, double* d_alpha, double* d_contact, double* d_grad, int32_t* d_iters,
-                      int32_t* d_status, int32_t n_dest, double* const* dest, int64_t record_offset, void* stream_)
+                      int32_t* d_status, int32_t n_dest, double* const* dest, int64_t record_offset, void* stream_,
+                      double* d_jac)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     dcol_shape_table* T = const_cast<dcol_shape_table*>(P->table);
@@ -524,6 +559,7 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
         BatchArgs a = { P->d_perm, g.first, g.count, d_pose1, d_pose2, tol, max_iter, flags,
                         d_alpha, d_contact, d_grad, d_iters, d_status, nullptr, n_dest, record_offset, {} };
         for (int d = 0; d < n_dest; ++d) a.dest[d] = dest[d];
+        a.jac = d_jac;
         cudaError_t e;
         if (!g.supported && !(flags & DCOL_FIX_CASE4)) {
             fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, st>>>(a);

@@ -1,0 +1,4 @@
+/* solution-Jacobian pair kernels whose first primitive is of class CLS_SPHERE */
+#include "dcol_kernels.cuh"
+
+DCOL_DEFINE_FIRST_CLASS_JAC(CLS_SPHERE)

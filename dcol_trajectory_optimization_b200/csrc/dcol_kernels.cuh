@@ -51,6 +51,7 @@ struct BatchArgs {
     int32_t n_dest;
     int64_t record_offset;
     double* dest[DCOL_MAX_DEST];
+    double* jac; /* [B][4][12] solution Jacobian (jacobian kernels only, otherwise null) */
 };
 
 /* one pair with the mu trace and the world-frame (x, s, z): the debug entry point */
@@ -69,8 +70,10 @@ struct GroupArgs {
 constexpr int kRecordWords = 14;
 constexpr int kStageBytes = (kThreads / 32) * 32 * kRecordWords * 8;
 
-template <class P1, class P2>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
+/* JAC: the specialisations that also write the solution Jacobian; separate kernels,
+ * compiled in their own translation units (dcol_jac_*.cu), so the hot kernels keep their register allocation */
+template <class P1, class P2, bool JAC = false>
+__global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
 {
     typedef Solver<P1, P2> S;
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -162,6 +165,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const __grid
             }
         }
     }
+    if (JAC) {
+        /* d(contact, alpha) / d[r1 p1 r2 p2] by an adjoint solve with the factor of the final reduced KKT matrix */
+        double* jp = a.b.jac + 48 * k;
+        if (st != DCOL_STATUS_OK || sv.jacobian(a.c1, a.c2, pose1, pose2, jp) != 0) {
+            for (int j = 0; j < 48; ++j) jp[j] = nan;
+        }
+    }
     if (a.b.trace) {
         TraceOut* out = a.b.trace;
         out->n = S::N;
@@ -179,7 +189,7 @@ struct GroupLaunch {
     BatchArgs args;
 };
 
-template <int C1, int C2>
+template <int C1, int C2, bool JAC = false>
 cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
 {
     typedef typename ClassPrim<C1>::type P1;
@@ -190,7 +200,7 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
     a.b = g.args;
     if (g.args.count <= 0) return cudaSuccess;
     const int64_t blocks = (g.args.count + kThreads - 1) / kThreads;
-    pair_kernel<P1, P2><<<(unsigned)blocks, kThreads, g.args.n_dest > 0 ? kStageBytes : 0, stream>>>(a);
+    pair_kernel<P1, P2, JAC><<<(unsigned)blocks, kThreads, g.args.n_dest > 0 ? kStageBytes : 0, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -208,8 +218,24 @@ template <> cudaError_t launch_first_class<CLS_PGON5>(int, const GroupLaunch&, c
 template <> cudaError_t launch_first_class<CLS_PGONN>(int, const GroupLaunch&, cudaStream_t);
 template <> cudaError_t launch_first_class<CLS_BOX>(int, const GroupLaunch&, cudaStream_t);
 template <> cudaError_t launch_first_class<CLS_ELLIPSOID>(int, const GroupLaunch&, cudaStream_t);
+/* the same dispatch for the Jacobian kernels (dcol_jac_*.cu) */
+template <int C1>
+cudaError_t launch_first_class_jac(int c2, const GroupLaunch& g, cudaStream_t stream);
+template <> cudaError_t launch_first_class_jac<CLS_POLY6>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_POLY8>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_POLYN>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_CAPSULE>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_CYLINDER>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_CONE>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_SPHERE>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_PGON5>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_PGONN>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_BOX>(int, const GroupLaunch&, cudaStream_t);
+template <> cudaError_t launch_first_class_jac<CLS_ELLIPSOID>(int, const GroupLaunch&, cudaStream_t);
 
-#define DCOL_DEFINE_FIRST_CLASS(C1)                                                              \
+#define DCOL_DEFINE_FIRST_CLASS(C1) DCOL_DEFINE_FIRST_CLASS_(C1, launch_first_class, false)
+#define DCOL_DEFINE_FIRST_CLASS_JAC(C1) DCOL_DEFINE_FIRST_CLASS_(C1, launch_first_class_jac, true)
+#define DCOL_DEFINE_FIRST_CLASS_(C1, FN, JAC)                                                    \
     namespace dcol {                                                                             \
     namespace {                                                                                  \
     struct LaunchFn_##C1 {                                                                       \
@@ -219,12 +245,12 @@ template <> cudaError_t launch_first_class<CLS_ELLIPSOID>(int, const GroupLaunch
         template <int A1, int A2>                                                                \
         void operator()()                                                                        \
         {                                                                                        \
-            err = launch_pair<A1, A2>(*g, stream);                                               \
+            err = launch_pair<A1, A2, JAC>(*g, stream);                                          \
         }                                                                                        \
     };                                                                                           \
     }                                                                                            \
     template <>                                                                                  \
-    cudaError_t launch_first_class<C1>(int c2, const GroupLaunch& g, cudaStream_t stream)        \
+    cudaError_t FN<C1>(int c2, const GroupLaunch& g, cudaStream_t stream)                        \
     {                                                                                            \
         LaunchFn_##C1 f = { &g, stream, cudaSuccess };                                           \
         if (!dispatch_class2<C1>(c2, f)) return cudaErrorInvalidValue;                           \

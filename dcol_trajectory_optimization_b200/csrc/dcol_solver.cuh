@@ -1206,6 +1206,165 @@ struct Solver {
         grad_block<P2>(w2, c2, CE2, b2, xw, Rf, pose2 + 3, Q2, grad + 6);
     }
 
+    /* ------------------------------------------------------------------------------------------------
+     * Solution Jacobian d(contact point, alpha) / d[r1 p1 r2 p2]  (Report.pdf
+     * section 2.3 eq. 4-6: differentiate the relaxed KKT system at the returned central-path point).
+     * EXTENSION: the reference only differentiates the frozen-(x, z) Lagrangian (proximity_gradient.py:8-88).
+     *
+     * With a symmetric linearisation of the complementarity condition, ds = -W^2 dz:
+     *     G^T dz = -dG^T z,   G dx + ds = -(dG x - dh)   =>   dx = -M^-1 (dG^T z + G^T W^-2 (dG x - dh)),
+     * M = G^T W^-2 G: the reduced KKT matrix of the Newton steps, rebuilt and factored at the final iterate.  Only
+     * four rows of dx are wanted, so the solve is an adjoint one: y_k = M^-1 e_k (four back-substitutions with the
+     * factor), v_k = W^-2 G y_k, and then row k is minus the pose derivative of the bilinear form
+     *     z^T G(theta) y_k + v_k^T (G(theta) x - h(theta))            (x, y_k, z, v_k frozen),
+     * i.e. two Lagrangian-like forms of exactly the kind gradient() differentiates analytically.
+     *
+     * Which W: on the orthant W^2 = s/z is the exact linearisation of s_i z_i = const.  On a second-order cone the
+     * Nesterov-Todd W^2 = eta^2 (2 wbar wbar^T - J) is the exact linearisation of s o z = mu e only ON the central
+     * path; the returned iterate is off-centre (the solver never re-centres, pdip.py:418-422), and there the NT
+     * scale eta^2 = sqrt(J(s)/J(z)) misstates the curvature of the cone's tangent plane by sqrt(eps_s/eps_z)
+     * (measured: contact-point rows off by factors of 2-6 under rotations).  The exact linearisation
+     * Arw(z) ds + Arw(s) dz = 0 acts on that tangent plane as ds = -(s_0/z_0) dz; keeping the NT direction wbar
+     * and replacing eta^2 by s_0/z_0 (equal to eta^2 on the central path, where both are mu/J(z)) gives a symmetric
+     * positive-definite W^2 with the same limit, so the Cholesky machinery of the solver is reused unchanged.
+     * Against central differences of 1e-12 solves it is as accurate as the unsymmetric exact linearisation
+     * (tests/test_jacobian.py). */
+    template <class P, class BL>
+    DCOL_HD static void jac_v(const P& p, const typename P::Const& c, int col_e, const BL& B, const double (&yt)[N],
+                              double (&vo)[P::NOA], double (&vq)[P::QA])
+    {
+        double rq[P::QA];
+        rows<P, false>(p, c, col_e, yt, vo, rq); /* G y (working frame: same rows) */
+        const int no = P::n_ort(c);
+        DCOL_UNROLL_ROWS
+        for (int i = 0; i < P::NO; ++i) {
+            if (P::dyn && i >= no) break;
+            const double winv = B.zo[i] * B.rinv[i];
+            vo[i] *= winv * winv; /* w_i^-2 = z_i / s_i */
+        }
+        if (P::Q > 0) {
+            /* W^-2 = (2 wh wh^T - J) / eta^2, as in pass_a */
+            const double ie2 = B.ieta * B.ieta;
+            double d = 0.0;
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) d += B.wh[i] * rq[i];
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) vq[i] = ie2 * (2.0 * d * B.wh[i] + (i == 0 ? -rq[i] : rq[i]));
+        }
+    }
+    /* g6 = d/d(r, p) [ z^T G(theta) yw + v^T (G(theta) xw - h(theta)) ] for one primitive at its WORLD pose pw
+     * (same chain rule as grad_block; the linear form has no r' dependence) */
+    template <class P, class BL>
+    DCOL_HD static void jac_block(const P& pw, const typename P::Const& c, int col_e, const BL& B,
+                                  const double (&vo)[P::NOA], const double (&vq)[P::QA], const double (&xw)[N],
+                                  const double (&yw)[N], const double (&Rf)[3][3], const double pm[3],
+                                  const double Qm[3][3], double* g6)
+    {
+        double az[P::NL], av[P::NL];
+        DCOL_UNROLL
+        for (int j = 0; j < P::NL; ++j) az[j] = av[j] = 0.0;
+        P::ort_apply_t(c, B.zo, az);
+        P::ort_apply_t(c, vo, av);
+        if (P::Q > 0 && !P::ball) {
+            P::soc_apply_t(c, B.zq, az);
+            P::soc_apply_t(c, vq, av);
+        }
+        double d[3], gr[3], Mq[3][3];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) d[i] = xw[i] - pw.rp[i];
+        double zwz[3] = { 0.0, 0.0, 0.0 }, zwv[3] = { 0.0, 0.0, 0.0 }, ex[3] = { 0.0, 0.0, 0.0 }, ey[3] = { 0.0, 0.0, 0.0 };
+        if (P::ball) {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                const double (&R)[3][3] = P::rot ? pw.Qp : Rf;
+                zwz[i] = R[i][0] * B.zq[1] + R[i][1] * B.zq[2] + R[i][2] * B.zq[3];
+                zwv[i] = R[i][0] * vq[1] + R[i][1] * vq[2] + R[i][2] * vq[3];
+            }
+            DCOL_UNROLL
+            for (int j = 0; j < P::NE; ++j) {
+                ex[j] = xw[col_e + j];
+                ey[j] = yw[col_e + j];
+            }
+        }
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i)
+            gr[i] = zwv[i] - (P::rot ? (pw.Qp[i][0] * av[0] + pw.Qp[i][1] * av[1] + pw.Qp[i][2] * av[2]) : av[i]);
+        double quz[3], quv[3], qex[3], qey[3];
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            quz[i] = c.Q_off[i][0] * az[0] + c.Q_off[i][1] * az[1] + c.Q_off[i][2] * az[2];
+            quv[i] = c.Q_off[i][0] * av[0] + c.Q_off[i][1] * av[1] + c.Q_off[i][2] * av[2];
+            qex[i] = c.Q_off[i][0] * ex[0] + c.Q_off[i][1] * ex[1] + c.Q_off[i][2] * ex[2];
+            qey[i] = c.Q_off[i][0] * ey[0] + c.Q_off[i][1] * ey[1] + c.Q_off[i][2] * ey[2];
+        }
+        DCOL_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            DCOL_UNROLL
+            for (int j = 0; j < 3; ++j)
+                Mq[i][j] = (P::rot ? d[i] * quv[j] + zwv[i] * qex[j] + yw[i] * quz[j] + zwz[i] * qey[j] : 0.0) +
+                           gr[i] * c.r_off[j];
+        }
+        g6[0] = gr[0];
+        g6[1] = gr[1];
+        g6[2] = gr[2];
+        dcm_derivative_contract(pm, Qm, Mq, g6 + 3);
+    }
+    /* jac[4][12]: rows (contact x, y, z, alpha), columns [r1 p1 r2 p2].  Call after a solve that returned
+     * DCOL_STATUS_OK (the NT scaling of the final iterate is still in the blocks).  Returns 0, or the status of
+     * the factorisation of M at the final iterate (jac is then left untouched). */
+    DCOL_HD int jacobian(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double* jac)
+    {
+        double L[N][N], Li[N];
+        if (F1::Q > 0) { /* eta^2 <- s_0 / z_0 (see above); pass_a and jac_v read the scale from the block */
+            b1.ieta = sqrt(b1.zq[0] / b1.sq[0]);
+            b1.eta = 1.0 / b1.ieta;
+        }
+        if (F2::Q > 0) {
+            b2.ieta = sqrt(b2.zq[0] / b2.sq[0]);
+            b2.eta = 1.0 / b2.ieta;
+        }
+        {
+            double M[N][N], va[N], vl[N];
+            DCOL_UNROLL
+            for (int i = 0; i < N; ++i) {
+                va[i] = vl[i] = 0.0;
+                DCOL_UNROLL
+                for (int j = 0; j < N; ++j) M[i][j] = 0.0;
+            }
+            pass_a<F1>(p1, c1, CE1, b1, x, M, va, vl);
+            pass_a<F2>(p2, c2, CE2, b2, x, M, va, vl);
+            if (int bad = chol(M, L, Li)) return bad;
+        }
+        double Q1[3][3], Q2[3][3], xw[N];
+        P1 w1;
+        P2 w2;
+        world_frames(c1, c2, pose1, pose2, w1, w2, Q1, Q2, xw);
+        const double (&Rf)[3][3] = kFrame2 ? w2.Qp : w1.Qp;
+        double Jt[4][12];
+        for (int k = 0; k < 4; ++k) { /* not unrolled: four passes over the same code */
+            double yt[N], yw[N];
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) yt[j] = (j == k) ? 1.0 : 0.0;
+            chol_solve(L, Li, yt);
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) yw[i] = Rf[i][0] * yt[0] + Rf[i][1] * yt[1] + Rf[i][2] * yt[2];
+            DCOL_UNROLL
+            for (int j = 3; j < N; ++j) yw[j] = yt[j];
+            double vo1[F1::NOA], vq1[F1::QA], vo2[F2::NOA], vq2[F2::QA];
+            jac_v<F1>(p1, c1, CE1, b1, yt, vo1, vq1);
+            jac_v<F2>(p2, c2, CE2, b2, yt, vo2, vq2);
+            jac_block<P1>(w1, c1, CE1, b1, vo1, vq1, xw, yw, Rf, pose1 + 3, Q1, Jt[k]);
+            jac_block<P2>(w2, c2, CE2, b2, vo2, vq2, xw, yw, Rf, pose2 + 3, Q2, Jt[k] + 6);
+        }
+        DCOL_UNROLL
+        for (int j = 0; j < 12; ++j) {
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) jac[12 * i + j] = -(Rf[i][0] * Jt[0][j] + Rf[i][1] * Jt[1][j] + Rf[i][2] * Jt[2][j]);
+            jac[36 + j] = -Jt[3][j];
+        }
+        return 0;
+    }
+
     /* world-frame (x, s, z) in the reference's row order [ort1; ort2; soc1; soc2] (debug entry point) */
     template <class P>
     DCOL_HD static void export_soc(const P& pw, const double (&Rf)[3][3], const double (&q)[P::QA], double* out)

@@ -51,6 +51,7 @@ class BatchResult:
     grad: object       # [B, 12]  d alpha / d [r1 p1 r2 p2], or None
     iters: object      # [B]      PDIP iterations taken
     status: object     # [B]      DCOL_STATUS_*
+    jac: object = None  # [B, 4, 12] d(contact x, y, z, alpha) / d [r1 p1 r2 p2] (``solve(want_jac=True)`` only)
 
     def summary(self) -> dict:
         """Per-batch counters (the reference has no logging inside the solver): how many pairs
@@ -176,11 +177,15 @@ class ProximityEngine:
         return Plan(self, torch.as_tensor(idx1), torch.as_tensor(idx2))
 
     def solve(self, plan: Plan, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
-              want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False) -> BatchResult:
+              want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False,
+              want_jac: bool = False) -> BatchResult:
         """Enqueue the solve of every pair of ``plan`` on the current CUDA stream.
 
         ``pose1``/``pose2``: float64 CUDA tensors ``[B, 6]`` (rows ``r, p``).  Returns CUDA tensors;
-        the call does not synchronise."""
+        the call does not synchronise.  ``want_jac`` (extension) also returns the
+        solution Jacobian ``jac[B, 4, 12]`` = d(contact point, alpha) / d[r1 p1 r2 p2], computed inside the solve
+        kernel by an adjoint solve with the factor of the final reduced KKT matrix
+        (``dcol_proximity_batch_jacobian``)."""
         import torch
         B = plan.size
         for name, t in (("pose1", pose1), ("pose2", pose2)):
@@ -193,10 +198,20 @@ class ProximityEngine:
                 contact=torch.empty((B, 3), dtype=torch.float64, device=dev) if want_contact else None,
                 grad=torch.empty((B, 12), dtype=torch.float64, device=dev) if want_grad else None,
                 iters=torch.empty(B, dtype=torch.int32, device=dev),
-                status=torch.empty(B, dtype=torch.int32, device=dev))
+                status=torch.empty(B, dtype=torch.int32, device=dev),
+                jac=torch.empty((B, 4, 12), dtype=torch.float64, device=dev) if want_jac else None)
         flags = ((WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
                  | (FIX_CASE4 if fix_case4 else 0))
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if want_jac:
+            if out.jac is None:
+                raise ValueError("want_jac needs out.jac ([B, 4, 12] float64 CUDA tensor)")
+            _lib.check(_lib.lib().dcol_proximity_batch_jacobian(
+                plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter), flags, out.alpha.data_ptr(),
+                out.contact.data_ptr() if out.contact is not None else None,
+                out.grad.data_ptr() if out.grad is not None else None, out.jac.data_ptr(), out.iters.data_ptr(),
+                out.status.data_ptr(), stream))
+            return out
         _lib.check(_lib.lib().dcol_proximity_batch_device(
             plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter), flags, out.alpha.data_ptr(),
             out.contact.data_ptr() if out.contact is not None else None,

@@ -134,6 +134,19 @@ int dcol_proximity_batch_device(const dcol_plan* plan, const double* d_pose1, co
                                 int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact,
                                 double* d_grad, int32_t* d_iters, int32_t* d_status, void* stream);
 
+/* EXTENSION (Report.pdf section 2.3 eq. 4-6; absent from the reference's code,
+ * which only differentiates the frozen-(x, z) Lagrangian, proximity/proximity_gradient.py:8-88):
+ * the same solve, plus the SOLUTION JACOBIAN
+ *   d_jac : [B][4][12]   rows: contact point x, y, z and alpha;  columns: [r1 p1 r2 p2]
+ * obtained by differentiating the relaxed KKT system at the returned iterate,
+ *   dx = -(G^T W^-2 G)^-1 (dG^T z + G^T W^-2 (dG x - dh)),
+ * as an adjoint solve (four right-hand sides e_k) with the Cholesky factor of the reduced KKT matrix at the
+ * final iterate, inside the solve kernel.  Row 3 agrees with d_grad up to O(mu) (envelope theorem); rows 0-2 are
+ * what contact-rich simulation needs.  NaN where status != 0.  d_contact / d_grad may be NULL without their flag. */
+int dcol_proximity_batch_jacobian(const dcol_plan* plan, const double* d_pose1, const double* d_pose2, double tol,
+                                  int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact,
+                                  double* d_grad, double* d_jac, int32_t* d_iters, int32_t* d_status, void* stream);
+
 /* Record mode, for multi-GPU use: every pair's results go out as ONE 112-byte record
  *     { double alpha; double grad[12]; int32 iters; int32 status; }
  * written in PLAN order (record i belongs to pair dcol_plan_perm()[i]) at dest[d] + 14 * (record_offset + i)

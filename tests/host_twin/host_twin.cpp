@@ -21,7 +21,8 @@ struct PairIn {
 };
 struct PairOut {
     double alpha, x[8], grad[12], s[2 * DCOL_MAX_FACES + 8], z[2 * DCOL_MAX_FACES + 8], mu[DCOL_MAX_ITER + 1];
-    int n, m, iters, status;
+    double jac[48];
+    int n, m, iters, status, want_jac;
 };
 
 struct RunOne {
@@ -51,6 +52,11 @@ struct RunOne {
         for (int j = 0; j < 12; ++j) out->grad[j] = NAN;
         if (st == 0 && in->want_grad) sv->gradient(c1, c2, in->pose1, in->pose2, out->grad);
         out->m = st == 0 ? sv->export_xsz(c1, c2, in->pose1, in->pose2, out->x, out->s, out->z) : 0;
+        for (int j = 0; j < 48; ++j) out->jac[j] = NAN;
+        if (st == 0 && out->want_jac) { /* after the export: jacobian() reuses the blocks' temporaries */
+            double J[48];
+            if (sv->jacobian(c1, c2, in->pose1, in->pose2, J) == 0) memcpy(out->jac, J, sizeof(J));
+        }
         delete sv;
     }
 };
@@ -70,6 +76,7 @@ void run_pair(const PairIn& in, PairOut& out, bool trace)
         out.n = out.m = 0;
         for (int j = 0; j < 8; ++j) out.x[j] = NAN;
         for (int j = 0; j < 12; ++j) out.grad[j] = NAN;
+        for (int j = 0; j < 48; ++j) out.jac[j] = NAN;
     }
 }
 
@@ -83,12 +90,14 @@ struct Job {
     int max_iter, want_grad, tid, nthreads;
     double *alpha, *contact, *grad;
     int32_t *iters, *status;
+    double* jac;
 };
 
 void* worker(void* arg)
 {
     const Job* J = (const Job*)arg;
     PairOut* out = new PairOut();
+    out->want_jac = J->jac != 0;
     for (int64_t c0 = (int64_t)J->tid * 64; c0 < J->B; c0 += (int64_t)J->nthreads * 64) {
         int64_t c1 = c0 + 64 < J->B ? c0 + 64 : J->B;
         for (int64_t k = c0; k < c1; ++k) {
@@ -100,6 +109,7 @@ void* worker(void* arg)
             J->status[k] = out->status;
             if (J->contact) for (int j = 0; j < 3; ++j) J->contact[3 * k + j] = out->x[j];
             if (J->grad) for (int j = 0; j < 12; ++j) J->grad[12 * k + j] = out->grad[j];
+            if (J->jac) for (int j = 0; j < 48; ++j) J->jac[48 * k + j] = out->jac[j];
         }
     }
     delete out;
@@ -110,10 +120,10 @@ void* worker(void* arg)
 
 extern "C" void dcol_twin_set_fix_case4(int on) { g_fix_case4 = on; }
 
-extern "C" int dcol_twin_batch(const dcol_shape* shapes, const double* A, const double* b, const int32_t* idx1,
-                               const int32_t* idx2, const double* pose1, const double* pose2, int64_t B, double tol,
-                               int max_iter, int threads, double* alpha, double* contact, double* grad,
-                               int32_t* iters, int32_t* status)
+static int twin_batch(const dcol_shape* shapes, const double* A, const double* b, const int32_t* idx1,
+                      const int32_t* idx2, const double* pose1, const double* pose2, int64_t B, double tol,
+                      int max_iter, int threads, double* alpha, double* contact, double* grad,
+                      int32_t* iters, int32_t* status, double* jac)
 {
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;
@@ -121,13 +131,31 @@ extern "C" int dcol_twin_batch(const dcol_shape* shapes, const double* A, const 
     Job jobs[256];
     for (int t = 0; t < threads; ++t) {
         Job j = { shapes, A, b, idx1, idx2, pose1, pose2, B, tol, max_iter, grad != 0, t, threads,
-                  alpha, contact, grad, iters, status };
+                  alpha, contact, grad, iters, status, jac };
         jobs[t] = j;
     }
     if (threads == 1) { worker(&jobs[0]); return 0; }
     for (int t = 0; t < threads; ++t) pthread_create(&tid[t], 0, worker, &jobs[t]);
     for (int t = 0; t < threads; ++t) pthread_join(tid[t], 0);
     return 0;
+}
+
+extern "C" int dcol_twin_batch(const dcol_shape* shapes, const double* A, const double* b, const int32_t* idx1,
+                               const int32_t* idx2, const double* pose1, const double* pose2, int64_t B, double tol,
+                               int max_iter, int threads, double* alpha, double* contact, double* grad,
+                               int32_t* iters, int32_t* status)
+{
+    return twin_batch(shapes, A, b, idx1, idx2, pose1, pose2, B, tol, max_iter, threads, alpha, contact, grad, iters,
+                      status, 0);
+}
+/* ... plus the solution Jacobian jac[B][4][12] (dcol_proximity_batch_jacobian) */
+extern "C" int dcol_twin_batch_jac(const dcol_shape* shapes, const double* A, const double* b, const int32_t* idx1,
+                                   const int32_t* idx2, const double* pose1, const double* pose2, int64_t B, double tol,
+                                   int max_iter, int threads, double* alpha, double* contact, double* grad,
+                                   int32_t* iters, int32_t* status, double* jac)
+{
+    return twin_batch(shapes, A, b, idx1, idx2, pose1, pose2, B, tol, max_iter, threads, alpha, contact, grad, iters,
+                      status, jac);
 }
 
 /* one pair with the mu trace and the world-frame (x, s, z) */
@@ -137,6 +165,7 @@ extern "C" int dcol_twin_pair(const dcol_shape* shapes, const double* A, const d
                               double* mu_trace)
 {
     PairOut* out = new PairOut();
+    out->want_jac = 0;
     PairIn in = { shapes + i1, shapes + i2, A, b, pose1, pose2, tol, DCOL_MAX_ITER, 1 };
     run_pair(in, *out, true);
     *alpha = out->alpha;

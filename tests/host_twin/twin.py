@@ -36,6 +36,8 @@ def lib():
         L.dcol_twin_batch.restype = C.c_int
         L.dcol_twin_batch.argtypes = [C.c_void_p, dp, dp, ip, ip, dp, dp, C.c_int64, C.c_double, C.c_int, C.c_int,
                                       dp, dp, dp, ip, ip]
+        L.dcol_twin_batch_jac.restype = C.c_int
+        L.dcol_twin_batch_jac.argtypes = L.dcol_twin_batch.argtypes + [dp]
         L.dcol_twin_pair.restype = C.c_int
         L.dcol_twin_pair.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, dp, dp, C.c_double, dp, dp, dp, dp,
                                      ip, ip, ip, dp, dp]
@@ -61,7 +63,7 @@ def _table(records, A, b):
 
 
 def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, max_iter=50, threads=None, want_grad=True,
-                fix_case4=False):
+                fix_case4=False, want_jac=False):
     records, A, b = _table(records, A, b)
     idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
     idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
@@ -71,12 +73,17 @@ def solve_batch(records, A, b, idx1, idx2, pose1, pose2, tol=1e-6, max_iter=50, 
     alpha, contact = np.empty(B), np.empty((B, 3))
     grad = np.empty((B, 12)) if want_grad else None
     iters, status = np.empty(B, np.int32), np.empty(B, np.int32)
+    jac = np.empty((B, 4, 12)) if want_jac else None
     lib().dcol_twin_set_fix_case4(1 if fix_case4 else 0)
-    lib().dcol_twin_batch(records.ctypes.data, _dp(A), _dp(b), _ip(idx1), _ip(idx2), _dp(pose1), _dp(pose2), B,
-                          float(tol), int(max_iter), int(threads or os.cpu_count() or 1), _dp(alpha), _dp(contact),
-                          _dp(grad) if want_grad else C.POINTER(C.c_double)(), _ip(iters), _ip(status))
+    args = [records.ctypes.data, _dp(A), _dp(b), _ip(idx1), _ip(idx2), _dp(pose1), _dp(pose2), B,
+            float(tol), int(max_iter), int(threads or os.cpu_count() or 1), _dp(alpha), _dp(contact),
+            _dp(grad) if want_grad else C.POINTER(C.c_double)(), _ip(iters), _ip(status)]
+    if want_jac:
+        lib().dcol_twin_batch_jac(*args, _dp(jac))
+    else:
+        lib().dcol_twin_batch(*args)
     lib().dcol_twin_set_fix_case4(0)
-    return dict(alpha=alpha, contact=contact, grad=grad, iters=iters, status=status)
+    return dict(alpha=alpha, contact=contact, grad=grad, iters=iters, status=status, jac=jac)
 
 
 def solve_pair(records, A, b, i1, i2, pose1, pose2, tol=1e-6):
