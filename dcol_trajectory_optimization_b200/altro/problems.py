@@ -54,7 +54,7 @@ class Problem:
     reg_max: float = 1e2
     max_iters: int = 3000
     max_linesearch_iters: int = 20
-    extra: dict = field(default_factory=dict)
+    extra: dict = field(default_factory=dict)   # extra["native"]: built-in system of the C++ host core (altro/native.py)
 
     @property
     def n_obs(self) -> int:
@@ -129,7 +129,8 @@ def piano_mover() -> Problem:
                    Qf=np.eye(nx), Xref=S["piano_Xref"], Uref=S["piano_Uref"], u_min=-200.0 * np.ones(nu),
                    u_max=200.0 * np.ones(nu), X0=S["piano_X0"], U0=S["piano_U0"],
                    victim=create_rect_prism(2.5, 0.15, 0.01), obstacles=obstacles, dynamics=dynamics,
-                   pose_of_state=pose_of_state, pose_jacobian=pose_jacobian, atol=4e-2)
+                   pose_of_state=pose_of_state, pose_jacobian=pose_jacobian, atol=4e-2,
+                   extra={"native": {"system": "piano"}})
 
 
 def cone_through_wall() -> Problem:
@@ -149,7 +150,8 @@ def cone_through_wall() -> Problem:
                    Uref=S["cone_Uref"], u_min=-20.0 * np.ones(nu), u_max=20.0 * np.ones(nu), X0=S["cone_X0"],
                    U0=S["cone_U0"], victim=ConeMRP(2.0, np.deg2rad(22)), obstacles=obstacles, dynamics=dynamics,
                    pose_of_state=lambda X: np.concatenate([X[..., 0:3], X[..., 6:9]], axis=-1),
-                   pose_jacobian=_pose_jac_6dof, atol=1e-1, extra={"mass": mass, "inertia": Jd})
+                   pose_jacobian=_pose_jac_6dof, atol=1e-1,
+                   extra={"mass": mass, "inertia": Jd, "native": {"system": "rigid_body", "mass": mass, "inertia": Jd}})
 
 
 def quadrotor() -> Problem:
@@ -181,7 +183,8 @@ def quadrotor() -> Problem:
                    Xref=S["quad_Xref"], Uref=S["quad_Uref"], u_min=-2000.0 * np.ones(nu), u_max=2000.0 * np.ones(nu),
                    X0=S["quad_X0"], U0=S["quad_U0"], victim=SphereMRP(0.25), obstacles=obstacles, dynamics=dynamics,
                    pose_of_state=lambda X: np.concatenate([X[..., 0:3], X[..., 6:9]], axis=-1),
-                   pose_jacobian=_pose_jac_6dof, atol=1e-2)
+                   pose_jacobian=_pose_jac_6dof, atol=1e-2,
+                   extra={"native": {"system": "quadrotor", "mass": mass, "inertia": Jd, "arm": L, "kf": kf, "km": km}})
 
 
 PROBLEMS = {"piano_mover": piano_mover, "coneThroughWall": cone_through_wall, "quadrotor": quadrotor}

@@ -14,7 +14,10 @@ dual / penalty updates ``:444-483``) with the same formulas, tolerances and upda
 * the cost of the current trajectory is computed once per pass, not once per trial (``ALTRO.py:215``), and the
   constraint values of the accepted trajectory are re-used for the dual update (``ALTRO.py:457-461``).
 
-The Riccati recursion itself is sequential over knots on 12x12 matrices and stays on the host (NumPy).
+The Riccati recursion itself is sequential over knots on 12x12 matrices and stays on the host: for the three
+built-in systems in the native core ``libdcol_altro.so`` (``csrc/altro_core.cpp``, ``include/dcol_altro.h``: RK4
+rollouts, forward-difference Jacobians + Riccati sweep, cost), otherwise — user-defined dynamics — in the NumPy
+functions below, which are also the cross-check of the native core (``tests/test_altro_native.py``).
 """
 from __future__ import annotations
 
@@ -92,6 +95,7 @@ class AltroResult:
     wall_s: float
     X_hist: list = field(default_factory=list)
     log: list = field(default_factory=list)
+    timing: dict = field(default_factory=dict)   # seconds: setup, constraints (engine calls), backward, rollouts, cost, teardown
 
 
 def _rk4(problem: Problem, X, U):
@@ -203,17 +207,35 @@ def _rollouts(problem: Problem, X, U, K, k, alphas):
 
 
 def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verbose: bool = False,
-                keep_history: bool = False) -> AltroResult:
+                keep_history: bool = False, native: bool | None = None) -> AltroResult:
     """Run AL-iLQR on ``problem``.  ``evaluator(victim_poses[M, 6], want_grad) -> (alpha[M, n_obs],
-    grad1[M, n_obs, 6] | None)`` defaults to the CUDA engine (:class:`EngineEvaluator`)."""
+    grad1[M, n_obs, 6] | None)`` defaults to the CUDA engine (:class:`EngineEvaluator`).  ``native``: run the
+    per-pass host work (rollouts, Jacobians + Riccati, cost) in the C++ core; default: whenever the problem is one
+    of its built-in systems (``problem.extra['native']``)."""
     t_start = time.perf_counter()
+    clock = time.perf_counter
+    tm = {"setup": 0.0, "constraints": 0.0, "backward": 0.0, "rollouts": 0.0, "cost": 0.0, "teardown": 0.0}
     own = evaluator is None
     if own:
         evaluator = EngineEvaluator(problem)
+    if native is None:
+        native = "native" in problem.extra
+    if native:
+        from .native import NativeCore
+        core = NativeCore(problem)
+        rk4_step = lambda x, u: core.rk4(x, u)[0]                                        # noqa: E731
+        backward = lambda *a: core.backward_pass(*a)                                     # noqa: E731
+        total_cost = lambda *a: core.total_cost(*a)                                      # noqa: E731
+        rollouts = lambda X_, U_, K_, k_, al: core.rollouts(X_, U_, K_, k_, al)          # noqa: E731
+    else:
+        rk4_step = lambda x, u: _rk4(problem, x, u)                                      # noqa: E731
+        backward = lambda *a: _backward_pass(problem, *a)                                # noqa: E731
+        total_cost = lambda *a: _total_cost(problem, *a)                                 # noqa: E731
+        rollouts = lambda X_, U_, K_, k_, al: _rollouts(problem, X_, U_, K_, k_, al)     # noqa: E731
     N, nx, nu, n_obs = problem.N, problem.nx, problem.nu, problem.n_obs
     X, U = problem.X0.copy(), problem.U0.copy()
     for t in range(N - 1):                                              # initial rollout, ALTRO.py:399-400
-        X[t + 1] = _rk4(problem, X[t], U[t])
+        X[t + 1] = rk4_step(X[t], U[t])
     mu = np.zeros((N - 1, 2 * nu))
     mux = np.zeros((N, n_obs))
     lambd = np.zeros(nx)
@@ -223,7 +245,17 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
     penalty_updates, converged, passes, J = 0, False, 0, np.nan
     pair_solves = calls = 0
 
+    tm["setup"] = clock() - t_start
+
     def constraints(Xs, want_grad):
+        nonlocal pair_solves, calls
+        t0 = clock()
+        try:
+            return _constraints(Xs, want_grad)
+        finally:
+            tm["constraints"] += clock() - t0
+
+    def _constraints(Xs, want_grad):
         nonlocal pair_solves, calls
         lead = Xs.shape[:-1]
         poses = problem.pose_of_state(Xs).reshape(-1, 6)
@@ -240,22 +272,30 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
     for itr in range(problem.max_iters):
         passes = itr + 1
         hx, ghx = constraints(X, True)                                   # ONE batched solve: values + gradients
-        K, k, delta_J = _backward_pass(problem, X, U, hx, ghx, mu, mux, lambd, rho, reg)
-        old_cost = float(_total_cost(problem, X, U, hx, mu, mux, lambd, rho))
+        t0 = clock()
+        K, k, delta_J = backward(X, U, hx, ghx, mu, mux, lambd, rho, reg)
+        t1 = clock()
+        old_cost = float(total_cost(X, U, hx, mu, mux, lambd, rho))
+        tm["backward"] += t1 - t0
+        tm["cost"] += clock() - t1
         alpha, accepted = 0.0, None
         if speculative:
-            Xn, Un = _rollouts(problem, X, U, K, k, ls_alphas)
+            t0 = clock()
+            Xn, Un = rollouts(X, U, K, k, ls_alphas)
+            tm["rollouts"] += clock() - t0
             hxn, _ = constraints(Xn, False)                              # ONE batched solve for all step sizes
-            costs = _total_cost(problem, Xn, Un, hxn, mu, mux, lambd, rho)
+            t0 = clock()
+            costs = total_cost(Xn, Un, hxn, mu, mux, lambd, rho)
+            tm["cost"] += clock() - t0
             better = np.nonzero(costs < old_cost)[0]
             if better.size:
                 c = int(better[0])
                 alpha, accepted = ls_alphas[c], (Xn[c].copy(), Un[c].copy(), hxn[c].copy(), float(costs[c]))
         else:
             for a in ls_alphas:
-                Xn, Un = _rollouts(problem, X, U, K, k, [a])
+                Xn, Un = rollouts(X, U, K, k, [a])
                 hxn, _ = constraints(Xn, False)
-                cost = float(_total_cost(problem, Xn, Un, hxn, mu, mux, lambd, rho)[0])
+                cost = float(total_cost(Xn, Un, hxn, mu, mux, lambd, rho)[0])
                 if cost < old_cost:
                     alpha, accepted = a, (Xn[0].copy(), Un[0].copy(), hxn[0].copy(), cost)
                     break
@@ -292,8 +332,10 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
                 break
             rho *= problem.phi
             penalty_updates += 1
+    t0 = clock()
     if own:
         evaluator.close()
+    tm["teardown"] = clock() - t0
     return AltroResult(X=X, U=U, passes=passes, converged=converged, cost=float(J), rho=rho,
                        penalty_updates=penalty_updates, pair_solves=pair_solves, batched_calls=calls,
-                       wall_s=time.perf_counter() - t_start, X_hist=hist, log=log)
+                       wall_s=time.perf_counter() - t_start, X_hist=hist, log=log, timing=tm)

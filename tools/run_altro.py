@@ -24,6 +24,8 @@ def run(names=("piano_mover", "coneThroughWall", "quadrotor"), repeats=2):
                 best = res
         line = {"scenario": name, "wall_s": best.wall_s, "passes": best.passes, "converged": best.converged,
                 "pair_solves": best.pair_solves, "batched_calls": best.batched_calls,
+                "host": "native core (libdcol_altro.so)" if "native" in PROBLEMS[name]().extra else "numpy",
+                "timing_s": {k: round(v, 4) for k, v in best.timing.items()},
                 "reference_python_wall_s": REF_WALL[name], "reference_julia_wall_s": JULIA_WALL[name]}
         gpath = os.path.join(ROOT, "tests", "golden", f"altro_{name}.npz")
         if os.path.exists(gpath):
