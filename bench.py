@@ -356,9 +356,11 @@ def main():
             "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,
-                         "traffic": {"dram_bytes_per_launch": 143.6e6, "pairs_per_launch": 209715,
-                                     "source": "profiles/r01_ncu_full_14kernels.md (ncu --set full, mean of 14 specialisations "
-                                               "at this size, captured with the contact point also written; algorithmic 212 B/pair = 44.5e6 B per launch)"},
+                         "traffic": 143.6e6,
+                         "traffic_detail": {"unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "pairs_per_launch": 209715,
+                                            "algorithmic_bytes_per_launch": 209715 * 212,
+                                            "source": "profiles/r01_ncu_full_14kernels.md (ncu --set full, mean of 14 specialisations "
+                                                      "at this size, captured with the contact point also written)"},
                          "kernel": f"dcol::pair_kernel<P1,P2> ({plans[0].n_groups} specialisations, {n_launches} launches per step)",
                          "kernel_ms_per_step": kernel_ms, "model_flops_per_pair": flops / B,
                          "peak_source": "dcol_measure_fp64_peak in this run (MEASURED_PEAKS.json has no FP64 entry)",
