@@ -13,6 +13,7 @@
 #define DCOL_KERNELS_CUH_
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "dcol_classes.cuh"
 
@@ -52,6 +53,7 @@ struct BatchArgs {
     int64_t record_offset;
     double* dest[DCOL_MAX_DEST];
     double* jac; /* [B][4][12] solution Jacobian (jacobian kernels only, otherwise null) */
+    int32_t ahead; /* threads of one resident wave (SMs x CTAs/SM x kThreads): L2 prefetch distance, 0 = off */
 };
 
 /* one pair with the mu trace and the world-frame (x, s, z): the debug entry point */
@@ -81,6 +83,18 @@ __global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(co
     const unsigned lanes = __ballot_sync(0xffffffffu, t < a.b.count);
     if (t >= a.b.count) return;
     const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + t] : a.b.first + t;
+#ifndef DCOL_NO_PREFETCH
+    /* A thread's only global reads are perm -> poses: two DEPENDENT DRAM latencies with nothing to overlap them
+     * (ncu: 11 % of the warp samples of a launch sit on the first use of the poses).  So every thread pulls the
+     * poses of the pair that the CTA taking over this slot one resident wave later will read into L2, and the perm
+     * entries of the wave after that, in the shadow of its own loads; later waves then start from L2 hits. */
+    int64_t ka = -1;
+    if (a.b.ahead > 0 && t + a.b.ahead < a.b.count) {
+        ka = a.b.perm ? (int64_t)a.b.perm[a.b.first + t + a.b.ahead] : a.b.first + t + a.b.ahead;
+        if (a.b.perm && t + 2 * (int64_t)a.b.ahead < a.b.count)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.perm + a.b.first + t + 2 * (int64_t)a.b.ahead));
+    }
+#endif
 
     double pose1[6], pose2[6];
 #pragma unroll
@@ -88,6 +102,14 @@ __global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(co
         pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
         pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
     }
+#ifndef DCOL_NO_PREFETCH
+    if (ka >= 0) { /* a 48-byte row can straddle two 32-byte sectors of different lines: touch both ends */
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose1 + 6 * ka));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose1 + 6 * ka + 5));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose2 + 6 * ka));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose2 + 6 * ka + 5));
+    }
+#endif
     S sv;
     PairResult<S::N> res;
 #ifdef DCOL_NO_RECORDS
@@ -189,6 +211,18 @@ struct GroupLaunch {
     BatchArgs args;
 };
 
+/* threads of one resident wave of pair_kernel CTAs on the current device (the kernels are register-limited to
+ * kMinBlocks CTAs per SM) */
+inline int resident_wave_threads()
+{
+    static const int off = getenv("DCOL_NO_PREFETCH") ? 1 : 0; /* A/B switch */
+    if (off) return 0;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return 0;
+    return sms * kMinBlocks * kThreads;
+}
+
 template <int C1, int C2, bool JAC = false>
 cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
 {
@@ -199,6 +233,7 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
     fill_const(*g.s2, g.A, g.b, a.c2);
     a.b = g.args;
     if (g.args.count <= 0) return cudaSuccess;
+    a.b.ahead = g.args.trace ? 0 : resident_wave_threads();
     const int64_t blocks = (g.args.count + kThreads - 1) / kThreads;
     pair_kernel<P1, P2, JAC><<<(unsigned)blocks, kThreads, g.args.n_dest > 0 ? kStageBytes : 0, stream>>>(a);
     return cudaGetLastError();
