@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-altro", action="store_true", help="skip the three ALTRO scenario solves (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-coherent", action="store_true", help="skip the coherent re-solve line (N = 1 only)")
     ap.add_argument("--no-jacobian", action="store_true", help="skip the solution-Jacobian throughput line (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -391,6 +392,38 @@ def main():
             line["jacobian"] = {"value": nj / (jms * 1e-3), "unit": UNIT, "pairs_per_step": nj, "ms_per_step": jms,
                                 "finite": bool(torch.isfinite(jout.jac).all()),
                                 "outputs": "alpha + grad[12] + jac[4][12] + iters + status (496 B/pair)"}
+        if world == 1 and not args.no_coherent:
+            # (new) temporally coherent re-solves, the ALTRO access pattern: the SAME pair list is solved again and again
+            # with slowly drifting poses (random walk, sigma per step), and after every solve the plan is re-ordered by that
+            # solve's iteration counts (dcol_plan_refine), so warps hold pairs of nearly equal count.  Every step solves
+            # poses it has never seen; the refine kernels are inside the timed region.  Not part of `value`.
+            nc, sigma, n_seq, n_warm = min(B, 1 << 21), 0.01, 8, 3
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(7)
+            seq, cur = [], d1[:nc].clone()
+            for _ in range(n_seq + n_warm):
+                cur = cur + sigma * torch.randn(cur.shape, generator=gen, device=dev, dtype=cur.dtype)
+                seq.append(cur)
+            rates = {}
+            for mode in ("plain", "refined"):
+                cplan = eng.plan(i1[:nc], i2[:nc])
+                cout = None
+                cev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                for s_, poses in enumerate(seq):
+                    if s_ == n_warm:
+                        cev[0].record()
+                    cout = eng.solve(cplan, poses, d2[:nc], want_contact=False, out=cout)
+                    if mode == "refined":
+                        cplan.refine(cout.iters)
+                cev[1].record()
+                torch.cuda.synchronize()
+                rates[mode] = nc * n_seq / (cev[0].elapsed_time(cev[1]) * 1e-3)
+                cplan.close()
+            line["coherent_resolve"] = {"value": rates["refined"], "value_without_refine": rates["plain"], "unit": UNIT,
+                                        "pairs_per_step": nc, "steps": n_seq, "pose_drift_sigma_per_step": sigma,
+                                        "failed_pairs_last_step": int((cout.status != 0).sum()),
+                                        "note": "fixed pair list, poses drift by a random walk; plan re-ordered after every "
+                                                "solve by that solve's iteration counts (dcol_plan_refine, inside the timed region)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)

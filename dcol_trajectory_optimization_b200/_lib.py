@@ -22,7 +22,7 @@ MAX_DEST, RECORD_WORDS = 8, 14
 #: every symbol include/dcol.h declares (checked by the CPU test-suite against the built library)
 SYMBOLS = (
     "dcol_version", "dcol_last_error", "dcol_device_count", "dcol_shape_table_create", "dcol_shape_table_destroy",
-    "dcol_plan_create", "dcol_plan_destroy", "dcol_plan_size", "dcol_plan_n_groups", "dcol_plan_n_launches",
+    "dcol_plan_create", "dcol_plan_destroy", "dcol_plan_size", "dcol_plan_n_groups", "dcol_plan_n_launches", "dcol_plan_refine",
     "dcol_proximity_batch_device", "dcol_proximity_batch_jacobian", "dcol_proximity_batch_host", "dcol_host_alloc",
     "dcol_host_free",
     "dcol_proximity_batch_records", "dcol_plan_perm", "dcol_device_alloc", "dcol_device_free", "dcol_ipc_export",
@@ -76,6 +76,8 @@ def lib():
     L.dcol_plan_n_groups.argtypes = [vp]
     L.dcol_plan_n_launches.restype = C.c_int32
     L.dcol_plan_n_launches.argtypes = [vp]
+    L.dcol_plan_refine.restype = C.c_int
+    L.dcol_plan_refine.argtypes = [vp, ip, vp]
     L.dcol_proximity_batch_device.restype = C.c_int
     L.dcol_proximity_batch_device.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_uint32, dp, dp, dp, ip, ip, vp]
     L.dcol_proximity_batch_jacobian.restype = C.c_int

@@ -116,6 +116,11 @@ struct dcol_plan {
     std::vector<int32_t> h_counts;
     std::vector<Group> groups;
     int32_t n_launches;
+    /* dcol_plan_refine: second permutation buffer (the two are swapped), group offsets and bin counters */
+    int32_t* d_perm_alt = nullptr;
+    int32_t* d_gstart = nullptr;   /* [n_groups + 1] first plan position of every group */
+    int32_t* d_bins = nullptr;     /* [2][n_groups * kRefineBins] histogram, cursors       */
+    int32_t refine_groups = -1;    /* group count d_gstart / d_bins were sized for          */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -191,6 +196,113 @@ __global__ void plan_scatter(const int32_t* __restrict__ idx1, const int32_t* __
         const int32_t key = a * n_shapes + c;
         const int32_t pos = priv ? base_of[key] + atomicAdd(&local[key], 1) : atomicAdd(&cursor[key], 1);
         perm[pos] = (int32_t)k;
+    }
+}
+
+/* ---- dcol_plan_refine: inside every group, order the pairs by the iteration count of their last solve ----
+ * A warp runs until its slowest pair converges (22-26 of 32 lanes are active on random batches).  A caller that
+ * re-solves the SAME pair list with slowly changing poses (every AL-iLQR pass, ALTRO.py:276-314) knows each pair's
+ * iteration count from the previous solve, and it barely changes from pass to pass; grouping pairs of equal count
+ * into the same warps removes most of the idle lanes.  Counting sort of the plan positions by
+ * (group, iterations descending, clamped to 0..63): histogram -> one-CTA exclusive scan -> scatter, all on the stream, no
+ * host sync. */
+constexpr int kRefineBins = 64;
+constexpr int kRefineMaxGroups = 1024;
+
+__device__ __forceinline__ int refine_group_of(const int32_t* __restrict__ gstart, int lo, int hi, int64_t pos)
+{
+    while (lo < hi) { /* last group whose first position is <= pos, in [lo, hi] */
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)gstart[mid] <= pos) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+/* longest first: the CTAs that finish a group's grid are then the short ones (a sorted-ascending order would leave the
+ * slowest warps for the tail of the grid) */
+__device__ __forceinline__ int32_t refine_bin(int32_t it)
+{
+    it = it < 0 ? 0 : (it >= kRefineBins ? kRefineBins - 1 : it);
+    return kRefineBins - 1 - it;
+}
+
+template <bool SCATTER>
+__global__ void refine_pass(const int32_t* __restrict__ perm, const int32_t* __restrict__ iters,
+                            const int32_t* __restrict__ gstart, int32_t n_groups, int64_t B, int32_t* __restrict__ bins,
+                            int32_t* __restrict__ perm_out)
+{
+    __shared__ int32_t local[kPlanSmemKeys];
+    __shared__ int32_t base_of[SCATTER ? kPlanSmemKeys : 1];
+    const int64_t base = (int64_t)blockIdx.x * kPlanTile;
+    const int64_t last = (base + kPlanTile <= B ? base + kPlanTile : B) - 1;
+    const int g_lo = refine_group_of(gstart, 0, n_groups - 1, base);
+    const int g_hi = refine_group_of(gstart, g_lo, n_groups - 1, last);
+    const int span = (g_hi - g_lo + 1) * kRefineBins;
+    const bool priv = span <= kPlanSmemKeys; /* a tile of consecutive plan positions touches few groups */
+    const int32_t bin0 = g_lo * kRefineBins;
+    if (priv) {
+        for (int i = threadIdx.x; i < span; i += kPlanThreads) local[i] = 0;
+        __syncthreads();
+    }
+    if (!SCATTER || priv) {
+        for (int o = threadIdx.x; o < kPlanTile; o += kPlanThreads) {
+            const int64_t pos = base + o;
+            if (pos >= B) break;
+            const int g = refine_group_of(gstart, g_lo, g_hi, pos);
+            const int32_t bin = g * kRefineBins + refine_bin(iters[perm[pos]]);
+            if (priv) atomicAdd(&local[bin - bin0], 1);
+            else atomicAdd(&bins[bin], 1);
+        }
+    }
+    if (!SCATTER) {
+        if (priv) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < span; i += kPlanThreads)
+                if (local[i]) atomicAdd(&bins[bin0 + i], local[i]);
+        }
+        return;
+    }
+    if (priv) { /* reserve one contiguous range per bin for this tile, then hand out tickets inside it */
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += kPlanThreads) {
+            base_of[i] = local[i] ? atomicAdd(&bins[bin0 + i], local[i]) : 0;
+            local[i] = 0;
+        }
+        __syncthreads();
+    }
+    for (int o = threadIdx.x; o < kPlanTile; o += kPlanThreads) {
+        const int64_t pos = base + o;
+        if (pos >= B) break;
+        const int g = refine_group_of(gstart, g_lo, g_hi, pos);
+        const int32_t pair = perm[pos];
+        const int32_t bin = g * kRefineBins + refine_bin(iters[pair]);
+        const int32_t dst = priv ? base_of[bin - bin0] + atomicAdd(&local[bin - bin0], 1) : atomicAdd(&bins[bin], 1);
+        perm_out[dst] = pair;
+    }
+}
+
+/* exclusive scan of the n bin counts into cursors (absolute plan positions: the bins are ordered by (group, iters) and
+ * the groups are contiguous); one CTA */
+__global__ void refine_scan(const int32_t* __restrict__ counts, int32_t n, int32_t* __restrict__ cursor)
+{
+    __shared__ int32_t part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    int32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += counts[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const int32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int32_t run = part[threadIdx.x] - s;
+    for (int i = lo; i < hi; ++i) {
+        cursor[i] = run;
+        run += counts[i];
     }
 }
 
@@ -464,6 +576,9 @@ void dcol_plan_destroy(dcol_plan* P)
     if (!P) return;
     DeviceGuard guard_(P->table->device);
     cudaFree(P->d_perm);
+    cudaFree(P->d_perm_alt);
+    cudaFree(P->d_gstart);
+    cudaFree(P->d_bins);
     cudaFree(P->d_counts);
     if (P->h_mapped) cudaFreeHost(P->h_mapped);
     delete P;
@@ -525,6 +640,43 @@ int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, cons
 }
 
 const int32_t* dcol_plan_perm(const dcol_plan* P) { return P ? P->d_perm : nullptr; }
+
+int dcol_plan_refine(dcol_plan* P, const int32_t* d_iters, void* stream_)
+{
+    if (!P || !d_iters) return fail(DCOL_E_ARG, "dcol_plan_refine: bad argument");
+    const int n_groups = (int)P->groups.size();
+    if (P->B == 0 || n_groups == 0) return 0;
+    if (n_groups > kRefineMaxGroups) return fail(DCOL_E_ARG, "dcol_plan_refine: at most 1024 groups");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCOL_DEVICE(P->table->device);
+    (void)cudaGetLastError();
+    const int n_bins = n_groups * kRefineBins;
+    if (!P->d_perm_alt) DCOL_CUDA(cudaMalloc(&P->d_perm_alt, sizeof(int32_t) * (size_t)P->capacity));
+    if (P->refine_groups != n_groups) { /* the host entry point rebuilds its cached plans: group lists change */
+        cudaFree(P->d_gstart);
+        cudaFree(P->d_bins);
+        P->d_gstart = P->d_bins = nullptr;
+        DCOL_CUDA(cudaMalloc(&P->d_gstart, sizeof(int32_t) * (size_t)(n_groups + 1)));
+        DCOL_CUDA(cudaMalloc(&P->d_bins, sizeof(int32_t) * 2 * (size_t)n_bins));
+        P->refine_groups = n_groups;
+    }
+    std::vector<int32_t> gstart(n_groups + 1);
+    for (int g = 0; g < n_groups; ++g) gstart[g] = (int32_t)P->groups[g].first;
+    gstart[n_groups] = (int32_t)P->B;
+    /* pageable source: the copy is staged before the call returns, so the vector may die */
+    DCOL_CUDA(cudaMemcpyAsync(P->d_gstart, gstart.data(), sizeof(int32_t) * gstart.size(), cudaMemcpyHostToDevice, stream));
+    DCOL_CUDA(cudaMemsetAsync(P->d_bins, 0, sizeof(int32_t) * (size_t)n_bins, stream));
+    const unsigned blocks = (unsigned)((P->B + kPlanTile - 1) / kPlanTile);
+    refine_pass<false><<<blocks, kPlanThreads, 0, stream>>>(P->d_perm, d_iters, P->d_gstart, n_groups, P->B, P->d_bins, nullptr);
+    DCOL_CUDA(cudaGetLastError());
+    refine_scan<<<1, 1024, 0, stream>>>(P->d_bins, n_bins, P->d_bins + n_bins);
+    DCOL_CUDA(cudaGetLastError());
+    refine_pass<true><<<blocks, kPlanThreads, 0, stream>>>(P->d_perm, d_iters, P->d_gstart, n_groups, P->B, P->d_bins + n_bins,
+                                                           P->d_perm_alt);
+    DCOL_CUDA(cudaGetLastError());
+    std::swap(P->d_perm, P->d_perm_alt);
+    return 0;
+}
 
 static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d_pose2, double tol, int32_t max_iter,
                       uint32_t flags, double* d_alpha, double* d_contact, double* d_grad, int32_t* d_iters,

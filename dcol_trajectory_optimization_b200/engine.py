@@ -125,6 +125,17 @@ class Plan:
             return torch.zeros(0, dtype=torch.int32, device=self.engine.device)
         return torch.as_tensor(_DevArray(ptr, (self.size,), "<i4"), device=self.engine.device).clone()
 
+    def refine(self, iters):
+        """Re-order the plan for the next solve of the same pair list: inside every group, pairs are sorted (longest first) by the
+        iteration counts ``iters`` (int32 CUDA tensor ``[size]``, pair order — ``BatchResult.iters`` of the previous
+        solve).  For callers that re-solve a fixed pair list with slowly changing poses (AL-iLQR passes): warps then
+        hold pairs of nearly equal iteration count.  Results are unaffected.  Enqueues on the current stream."""
+        import torch
+        if not (iters.is_cuda and iters.dtype == torch.int32 and iters.is_contiguous() and iters.numel() == self.size):
+            raise ValueError(f"iters must be a contiguous int32 CUDA tensor of {self.size} elements")
+        stream = torch.cuda.current_stream(self.engine.device).cuda_stream
+        _lib.check(_lib.lib().dcol_plan_refine(self._handle, iters.data_ptr(), stream))
+
     def close(self):
         if getattr(self, "_handle", None):
             _lib.lib().dcol_plan_destroy(self._handle)

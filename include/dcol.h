@@ -121,6 +121,15 @@ int32_t dcol_plan_n_groups(const dcol_plan* plan);
 /* Kernel launches one solve over this plan enqueues. */
 int32_t dcol_plan_n_launches(const dcol_plan* plan);
 
+/* (new) Re-order the plan for the NEXT solve of the same pair list: inside every group, pairs are sorted by
+ * descending d_iters[pair] (DEVICE pointer, pair order: the iters[] array a previous solve of this plan wrote).  A warp runs
+ * until its slowest pair converges; a caller that re-solves a fixed pair list with slowly changing poses (every
+ * AL-iLQR pass re-evaluates the same victim x obstacle constraints, ALTRO.py:276-314) gets warps of equal iteration
+ * count this way.  Results are unaffected (same pairs, same outputs at the same indices); only the order in which
+ * threads take pairs changes.  Enqueues on `stream` without synchronising; calls on one plan (solve, refine) must be
+ * stream-ordered; dcol_plan_perm() changes.  At most 1024 groups. */
+int dcol_plan_refine(dcol_plan* plan, const int32_t* d_iters, void* stream);
+
 /* Solve every pair of the plan.  All pointers are DEVICE pointers; the call only enqueues work
  * on `stream` (a cudaStream_t, may be NULL for the default stream).
  *   pose1, pose2 : [B][6] rows (r, p)
