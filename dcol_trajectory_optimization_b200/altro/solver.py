@@ -206,6 +206,26 @@ def _rollouts(problem: Problem, X, U, K, k, alphas):
     return Xn, Un
 
 
+class NumpyCore:
+    """The per-pass host work in NumPy, for user-defined dynamics (``Problem.dynamics`` is any vectorised callable);
+    same interface as :class:`native.NativeCore`, which runs the reference's three systems in C++."""
+
+    def __init__(self, problem: Problem):
+        self.problem = problem
+
+    def rk4(self, X, U):
+        return _rk4(self.problem, np.atleast_2d(X), np.atleast_2d(U))
+
+    def rollouts(self, X, U, K, k, alphas):
+        return _rollouts(self.problem, X, U, K, k, alphas)
+
+    def backward_pass(self, X, U, hx, ghx, mu, mux, lambd, rho, reg):
+        return _backward_pass(self.problem, X, U, hx, ghx, mu, mux, lambd, rho, reg)
+
+    def total_cost(self, X, U, hx, mu, mux, lambd, rho):
+        return _total_cost(self.problem, X, U, hx, mu, mux, lambd, rho)
+
+
 def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verbose: bool = False,
                 keep_history: bool = False, native: bool | None = None) -> AltroResult:
     """Run AL-iLQR on ``problem``.  ``evaluator(victim_poses[M, 6], want_grad) -> (alpha[M, n_obs],
@@ -223,19 +243,12 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
     if native:
         from .native import NativeCore
         core = NativeCore(problem)
-        rk4_step = lambda x, u: core.rk4(x, u)[0]                                        # noqa: E731
-        backward = lambda *a: core.backward_pass(*a)                                     # noqa: E731
-        total_cost = lambda *a: core.total_cost(*a)                                      # noqa: E731
-        rollouts = lambda X_, U_, K_, k_, al: core.rollouts(X_, U_, K_, k_, al)          # noqa: E731
     else:
-        rk4_step = lambda x, u: _rk4(problem, x, u)                                      # noqa: E731
-        backward = lambda *a: _backward_pass(problem, *a)                                # noqa: E731
-        total_cost = lambda *a: _total_cost(problem, *a)                                 # noqa: E731
-        rollouts = lambda X_, U_, K_, k_, al: _rollouts(problem, X_, U_, K_, k_, al)     # noqa: E731
+        core = NumpyCore(problem)
     N, nx, nu, n_obs = problem.N, problem.nx, problem.nu, problem.n_obs
     X, U = problem.X0.copy(), problem.U0.copy()
     for t in range(N - 1):                                              # initial rollout, ALTRO.py:399-400
-        X[t + 1] = rk4_step(X[t], U[t])
+        X[t + 1] = core.rk4(X[t], U[t])[0]
     mu = np.zeros((N - 1, 2 * nu))
     mux = np.zeros((N, n_obs))
     lambd = np.zeros(nx)
@@ -273,19 +286,19 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
         passes = itr + 1
         hx, ghx = constraints(X, True)                                   # ONE batched solve: values + gradients
         t0 = clock()
-        K, k, delta_J = backward(X, U, hx, ghx, mu, mux, lambd, rho, reg)
+        K, k, delta_J = core.backward_pass(X, U, hx, ghx, mu, mux, lambd, rho, reg)
         t1 = clock()
-        old_cost = float(total_cost(X, U, hx, mu, mux, lambd, rho))
+        old_cost = float(core.total_cost(X, U, hx, mu, mux, lambd, rho))
         tm["backward"] += t1 - t0
         tm["cost"] += clock() - t1
         alpha, accepted = 0.0, None
         if speculative:
             t0 = clock()
-            Xn, Un = rollouts(X, U, K, k, ls_alphas)
+            Xn, Un = core.rollouts(X, U, K, k, ls_alphas)
             tm["rollouts"] += clock() - t0
             hxn, _ = constraints(Xn, False)                              # ONE batched solve for all step sizes
             t0 = clock()
-            costs = total_cost(Xn, Un, hxn, mu, mux, lambd, rho)
+            costs = core.total_cost(Xn, Un, hxn, mu, mux, lambd, rho)
             tm["cost"] += clock() - t0
             better = np.nonzero(costs < old_cost)[0]
             if better.size:
@@ -293,9 +306,9 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
                 alpha, accepted = ls_alphas[c], (Xn[c].copy(), Un[c].copy(), hxn[c].copy(), float(costs[c]))
         else:
             for a in ls_alphas:
-                Xn, Un = rollouts(X, U, K, k, [a])
+                Xn, Un = core.rollouts(X, U, K, k, [a])
                 hxn, _ = constraints(Xn, False)
-                cost = float(total_cost(Xn, Un, hxn, mu, mux, lambd, rho)[0])
+                cost = float(core.total_cost(Xn, Un, hxn, mu, mux, lambd, rho)[0])
                 if cost < old_cost:
                     alpha, accepted = a, (Xn[0].copy(), Un[0].copy(), hxn[0].copy(), cost)
                     break

@@ -62,6 +62,15 @@ def test_altro_trajectory_parity_cpu(oracle, name):
     _check(name, res, g)
 
 
+def test_numpy_host_core_still_matches_the_reference(oracle):
+    """altro_solve(native=False): the NumPy implementation of the per-pass host work (user-defined dynamics)."""
+    from dcol_trajectory_optimization_b200.altro import PROBLEMS, altro_solve
+    g = _golden("piano_mover")
+    problem = PROBLEMS["piano_mover"]()
+    res = altro_solve(problem, evaluator=_oracle_evaluator(problem, oracle), native=False)
+    _check("piano_mover", res, g)
+
+
 def test_speculative_line_search_equals_sequential(oracle):
     from dcol_trajectory_optimization_b200.altro import PROBLEMS, altro_solve
     problem = PROBLEMS["piano_mover"]()
