@@ -130,6 +130,41 @@ def cpu_baseline(n_target_seconds=12.0, threads=None, seed=1234):
                       f"itself runs ~1e2 calls/s/core (BASELINE.md section 2), this C port ~6e4"}
 
 
+def cpu_baseline_python(single=1000, per_worker=200, timeout=600):
+    """The UNMODIFIED Python reference (baseline/_ref, installed by baseline/install_ref.py) timed on this box's host
+    cores in a subprocess: proximity_gradient on the head of the config-4 batch, one process and a fork pool of
+    os.cpu_count() workers.  Returns (dict for the JSON line, path of the saved outputs)."""
+    import tempfile
+    script = os.path.join(ROOT, "baseline", "time_reference.py")
+    check = os.path.join(tempfile.gettempdir(), f"dcol_ref_check_{os.getpid()}.npz")
+    try:
+        r = subprocess.run([sys.executable, "-W", "ignore", script, "--single", str(single), "--per-worker", str(per_worker),
+                            "--check", check], capture_output=True, text=True, timeout=timeout)
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"unavailable": f"baseline/time_reference.py failed: {exc!r}"[:300]}, None
+    return out, (check if os.path.exists(check) else None)
+
+
+def parity_vs_python_reference(check_path, device=0):
+    """alpha / gradient of the CUDA path against what the unmodified Python reference just computed on this box for
+    the same pairs (the head of the exact-sequence config-4 batch)."""
+    import dcol_trajectory_optimization_b200 as d
+    from dcol_trajectory_optimization_b200 import workloads as W
+    from dcol_trajectory_optimization_b200.shapes import flatten_shapes
+    ref = np.load(check_path)
+    n = len(ref["alpha"])
+    shapes, i1, i2, p1, p2 = W.config4_batch(n, seed=1234, exact=True)
+    eng = d.ProximityEngine(flatten_shapes(shapes), device=device)
+    res = eng.solve_host(i1, i2, p1, p2)
+    eng.close()
+    a_err = np.abs(res.alpha - ref["alpha"]) / np.maximum(np.abs(ref["alpha"]), 1.0)
+    g_err = np.abs(res.grad - ref["grad"]).max(axis=1) / np.abs(ref["grad"]).max(axis=1)
+    return {"pairs": n, "failed_pairs": int((res.status != 0).sum()), "max_alpha_rel_err": float(a_err.max()),
+            "max_grad_rel_err": float(g_err.max()), "bars": {"alpha": 1e-8, "grad": 1e-6},
+            "note": "reference gradient is a forward finite difference (h = 2^-26): its own noise is up to 5.4e-7"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
     itself is pure Python and cannot be compiled into oracle/_ref), all host threads."""
@@ -157,6 +192,10 @@ def run_reference(args):
                                        f"gradient), {threads} threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_python_reference:
+        # the reference itself (pure Python, ~1e2 calls/s/core): reported next to the port, which stays the arm's
+        # `value` because it is the STRONGER baseline (same algorithm in C on all cores)
+        line["cpu_baseline_python"], _ = cpu_baseline_python()
     print(json.dumps(line), flush=True)
 
 
@@ -174,6 +213,7 @@ def main():
     ap.add_argument("--workload", default="config4", choices=["config4", "config5"])
     ap.add_argument("--no-altro", action="store_true", help="skip the three ALTRO scenario solves (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true", help="skip timing the unmodified Python reference (baseline/_ref)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-coherent", action="store_true", help="skip the coherent re-solve line (N = 1 only)")
     ap.add_argument("--no-jacobian", action="store_true", help="skip the solution-Jacobian throughput line (N = 1 only)")
@@ -243,7 +283,7 @@ def main():
         plan_perm = plans[0].perm()
 
         def step():
-            eng.solve_records(plans[0], d1, d2, peer.dest_ptrs, multicast=peer.multicast)
+            eng.solve_records(plans[0], d1, d2, peer.begin_step(), multicast=peer.multicast)   # double-buffered slots
             peer.handshake()
     else:
         pipe = parallel.GatherPipeline(bounds, world if mode == "nccl" else 1, dev, with_contact=False)
@@ -287,12 +327,44 @@ def main():
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = B * world / (ms_per_step * 1e-3)
 
-    if mode == "fused":                     # read this rank's records back out of a PEER's view of them: slot `rank`
+    gather_check = None
+    if mode == "fused":
+        # Is rank s's slot of MY gathered buffer exactly what rank s computed?  Every rank solves its own batch once more
+        # through the NON-fused array-mode call (separate output arrays, no peer stores), packs those results into records
+        # in plan order, and publishes (a) two 64-bit checksums of all B records and (b) its first 65,536 records, through
+        # NCCL.  Every rank then compares EVERY slot of its gathered buffer with the owner's checksums (all records) and
+        # sample (bit for bit); the verdict is the AND over ranks.
         from dcol_trajectory_optimization_b200.engine import records_to_result
-        chk = torch.zeros(1, dtype=torch.float64, device=dev)
+
+        def checksums(rec):
+            x = rec.contiguous().view(torch.int64).reshape(-1)
+            wgt = torch.arange(x.numel(), device=x.device, dtype=torch.int64) % 1000003 + 1
+            return torch.stack([x.sum(), (x * wgt).sum()])          # int64 arithmetic wraps
+
+        ref = eng.solve(plans[0], d1, d2, want_contact=False)
+        pl = plan_perm.long()
+        rec_ref = torch.empty((B, parallel.WORDS_PER_PAIR), dtype=torch.float64, device=dev)
+        rec_ref[:, 0], rec_ref[:, 1:13] = ref.alpha[pl], ref.grad[pl]
+        rec_ref[:, 13] = (ref.iters[pl].long() | (ref.status[pl].long() << 32)).view(torch.float64)
+        n_s = min(B, 1 << 16)
+        cs_all = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        sm_all = [torch.empty((n_s, parallel.WORDS_PER_PAIR), dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(cs_all, checksums(rec_ref))
+        dist.all_gather(sm_all, rec_ref[:n_s].contiguous())
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        for r in range(world):              # slot r of my gathered buffer was filled by rank r's kernel
+            slot = peer.gathered[r]
+            good = torch.equal(checksums(slot), cs_all[r]) and torch.equal(slot[:n_s].contiguous().view(torch.int64),
+                                                                           sm_all[r].view(torch.int64))
+            if not good:
+                ok.zero_()
+                print(f"# rank {rank}: slot {r} of the gathered buffer differs from rank {r}'s own results", file=sys.stderr, flush=True)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_check = {"gather_verified": bool(int(ok)), "slots_checked": world,
+                        "how": f"every rank compared every slot of its gathered buffer with the owner's non-fused array-mode "
+                               f"re-solve: two 64-bit checksums over all {B} records per slot + the first {n_s} records bit for bit"}
         mine = [records_to_result(peer.gathered[rank], plan_perm)]
-        for r in range(world):              # every slot of my gathered buffer was filled by rank r's kernel
-            chk += (records_to_result(peer.gathered[r]).status != 0).sum()
+        del ref, rec_ref, sm_all
     else:
         mine = pipe.rank_results(rank)      # nccl: this rank's records out of the gathered buffers
     iters = torch.cat([r.iters for r in mine]).cpu().numpy()
@@ -339,7 +411,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.workload == "config4" else WORKLOAD5, "pairs_per_gpu": B, "type_pairs": plans[0].n_groups,
+            "config": {"workload": WORKLOAD if args.workload == "config4" else WORKLOAD5, "pairs_per_gpu": B, "pairs_per_step": B * world,
+                       "reference_arm_pairs_per_step": args.ref_pairs,
+                       "same_config_note": "the --impl reference arm runs a bounded sample of the same workload per step (the metric is a rate)",
+                       "type_pairs": plans[0].n_groups,
                        "mean_pdip_iters": float(iters.mean()), "failed_pairs": n_fail,
                        "l2": "inputs larger than L2 (805 MB of poses per step at the default size)",
                        "plan": "pairs grouped by shape pair once (device counting sort), plan reused by every step, as ALTRO "
@@ -353,6 +428,7 @@ def main():
                                       "nccl": f"all_gather_into_tensor of the 112 B/pair records, {n_chunks} chunk(s) per step"}[mode],
                        "parallelism": f"batch sharded over {world} GPU(s), one process per GPU"},
             "clocks": clocks,
+            **(gather_check or {}),
             "e2e": e2e,
             "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
@@ -426,6 +502,11 @@ def main():
                                                 "solve by that solve's iteration counts (dcol_plan_refine, inside the timed region)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if not args.no_python_reference:
+                line["cpu_baseline_python"], check = cpu_baseline_python()
+                if check:
+                    line["parity_vs_python_reference"] = parity_vs_python_reference(check, local_rank)
+                    os.remove(check)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

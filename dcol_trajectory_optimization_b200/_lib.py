@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DCOL_LIB") or os.path.join(HERE, "libdcol_b200.so")   # DCOL_LIB: build experiments
 CSRC = os.path.join(HERE, "csrc")
 
-WANT_CONTACT, WANT_GRAD, FIX_CASE4, DEST_MULTICAST = 1, 2, 4, 8
+WANT_CONTACT, WANT_GRAD, FIX_CASE4, DEST_MULTICAST, ONE_PAIR_PER_THREAD, WANT_GRAD1, LANE_REFILL = 1, 2, 4, 8, 16, 32, 64
 MAX_ITER = 50
 MAX_M, MAX_N = 72, 8
 MAX_DEST, RECORD_WORDS = 8, 14

@@ -61,6 +61,8 @@ struct DeviceGuard {
     DeviceGuard guard_(device);                                               \
     if (guard_.err != cudaSuccess) return fail_cuda(guard_.err, "cudaSetDevice")
 
+constexpr uint32_t kSolveFlags = DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4 | DCOL_ONE_PAIR_PER_THREAD | DCOL_WANT_GRAD1 | DCOL_LANE_REFILL;
+
 struct Group {
     int32_t i1, i2;
     int64_t first, count;
@@ -338,8 +340,10 @@ __global__ void fill_unsupported(BatchArgs b)
     b.status[k] = DCOL_STATUS_UNSUPPORTED;
     b.iters[k] = 0;
     b.alpha[k] = nan;
-    if (b.flags & DCOL_WANT_GRAD)
-        for (int j = 0; j < 12; ++j) b.grad[12 * k + j] = nan;
+    if (b.flags & DCOL_WANT_GRAD) {
+        const int gw = (b.flags & DCOL_WANT_GRAD1) ? 6 : 12;
+        for (int j = 0; j < gw; ++j) b.grad[gw * k + j] = nan;
+    }
 }
 
 /* FP64 FMA peak: 8 independent chains per thread, no memory traffic */
@@ -598,7 +602,8 @@ int dcol_proximity_batch_device(const dcol_plan* P, const double* d_pose1, const
 {
     if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_device: null plan");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
-    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4)) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~kSolveFlags) return fail(DCOL_E_ARG, "unknown flag");
+    if ((flags & DCOL_WANT_GRAD1) && !(flags & DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "DCOL_WANT_GRAD1 needs DCOL_WANT_GRAD");
     if (P->B == 0) return 0;
     if (!d_pose1 || !d_pose2 || !d_alpha || !d_iters || !d_status || ((flags & DCOL_WANT_CONTACT) && !d_contact) ||
         ((flags & DCOL_WANT_GRAD) && !d_grad))
@@ -613,7 +618,8 @@ int dcol_proximity_batch_jacobian(const dcol_plan* P, const double* d_pose1, con
 {
     if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_jacobian: null plan");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
-    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4)) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~kSolveFlags) return fail(DCOL_E_ARG, "unknown flag");
+    if ((flags & DCOL_WANT_GRAD1) && !(flags & DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "DCOL_WANT_GRAD1 needs DCOL_WANT_GRAD");
     if (P->B == 0) return 0;
     if (!d_pose1 || !d_pose2 || !d_alpha || !d_jac || !d_iters || !d_status || ((flags & DCOL_WANT_CONTACT) && !d_contact) ||
         ((flags & DCOL_WANT_GRAD) && !d_grad))
@@ -626,7 +632,7 @@ int dcol_proximity_batch_records(const dcol_plan* P, const double* d_pose1, cons
                                  int32_t max_iter, uint32_t flags, int32_t n_dest, double* const* dest,
                                  int64_t record_offset, double* d_contact, void* stream_)
 {
-    if (flags & ~(uint32_t)(DCOL_FIX_CASE4 | DCOL_DEST_MULTICAST)) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~(uint32_t)(DCOL_FIX_CASE4 | DCOL_DEST_MULTICAST | DCOL_ONE_PAIR_PER_THREAD | DCOL_LANE_REFILL)) return fail(DCOL_E_ARG, "unknown flag");
     if ((flags & DCOL_DEST_MULTICAST) && n_dest != 1) return fail(DCOL_E_ARG, "a multicast destination must be the only one");
     if (!P) return fail(DCOL_E_ARG, "dcol_proximity_batch_records: null plan");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
@@ -738,7 +744,8 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
     dcol_shape_table* T = const_cast<dcol_shape_table*>(T_);
     if (!T || B < 0) return fail(DCOL_E_ARG, "dcol_proximity_batch_host: bad argument");
     if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
-    if (flags & ~(uint32_t)(DCOL_WANT_CONTACT | DCOL_WANT_GRAD | DCOL_FIX_CASE4)) return fail(DCOL_E_ARG, "unknown flag");
+    if (flags & ~kSolveFlags) return fail(DCOL_E_ARG, "unknown flag");
+    if ((flags & DCOL_WANT_GRAD1) && !(flags & DCOL_WANT_GRAD)) return fail(DCOL_E_ARG, "DCOL_WANT_GRAD1 needs DCOL_WANT_GRAD");
     if (B == 0) return 0;
     if (!idx1 || !idx2 || !pose1 || !pose2 || !alpha || !iters || !status || ((flags & DCOL_WANT_CONTACT) && !contact) ||
         ((flags & DCOL_WANT_GRAD) && !grad))
@@ -753,6 +760,7 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
         if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
     }
+    const int64_t gw = (flags & DCOL_WANT_GRAD1) ? 6 : 12; /* doubles of gradient per pair */
     int64_t kChunk = 1 << 20; /* measured on B200 + PCIe 5 (chunks of 2^18..2^22): 2^20 pairs gives the best overlap */
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
@@ -814,7 +822,7 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         if (flags & DCOL_WANT_CONTACT)
             DCOL_CUDA(cudaMemcpyAsync(contact + 3 * k0, S.contact, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s_out));
         if (flags & DCOL_WANT_GRAD)
-            DCOL_CUDA(cudaMemcpyAsync(grad + 12 * k0, S.grad, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, s_out));
+            DCOL_CUDA(cudaMemcpyAsync(grad + gw * k0, S.grad, sizeof(double) * gw * n, cudaMemcpyDeviceToHost, s_out));
         DCOL_CUDA(cudaEventRecord(T->ev_out[slot], s_out));
     }
     cudaError_t e = cudaStreamSynchronize(s_out);

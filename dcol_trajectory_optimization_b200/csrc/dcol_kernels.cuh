@@ -54,6 +54,7 @@ struct BatchArgs {
     double* dest[DCOL_MAX_DEST];
     double* jac; /* [B][4][12] solution Jacobian (jacobian kernels only, otherwise null) */
     int32_t ahead; /* threads of one resident wave (SMs x CTAs/SM x kThreads): L2 prefetch distance, 0 = off */
+    int32_t per_warp; /* lane-refill kernel: plan positions owned by one warp */
 };
 
 /* one pair with the mu trace and the world-frame (x, s, z): the debug entry point */
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(co
     double g[12];
     if (want_grad) {
         if (st == DCOL_STATUS_OK) {
-            sv.gradient(a.c1, a.c2, pose1, pose2, g);
+            sv.gradient(a.c1, a.c2, pose1, pose2, g, !(a.b.flags & DCOL_WANT_GRAD1));
         } else {
 #pragma unroll
             for (int j = 0; j < 12; ++j) g[j] = nan;
@@ -146,8 +147,13 @@ __global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(co
         a.b.iters[k] = res.iters;
         a.b.alpha[k] = alpha;
         if (want_grad) {
+            if (a.b.flags & DCOL_WANT_GRAD1) {
 #pragma unroll
-            for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+                for (int j = 0; j < 6; ++j) a.b.grad[6 * k + j] = g[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+            }
         }
     } else {
         /* Record mode.  A warp's records are contiguous in plan order: transpose them through shared memory
@@ -202,6 +208,372 @@ __global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(co
     }
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Lane-refill kernel.  pair_kernel above gives a thread ONE pair, so a warp runs until its slowest pair converges:
+ * per-pair iteration counts have a long right tail (config 4: mean 8.1, mean of the per-warp maximum 11.2) and
+ * 22-26 of 32 lanes are active on average (profiles/r01_ncu_final_8kernels.md).  Iteration counts cannot be
+ * predicted from the geometry (sorting by mu_0, mu_1 or alpha moves lane efficiency from 0.72 to 0.74), so the
+ * lanes are kept busy dynamically instead:
+ *
+ *   - a warp owns a contiguous chunk of plan positions (per_warp pairs) and a pool of 32 state slots in shared memory;
+ *   - PHASE (convergent, all 32 lanes): lane j runs the epilogue (alpha, contact point, gradient, stores) of the
+ *     finished pair parked in slot j, then initialises a new pair (pose -> working frame, initial point, NT scaling of
+ *     iteration 0) and parks its loop-carried state in slot j as FRESH;
+ *   - TRIP (all lanes that hold a pair): one Newton step + the scaling / convergence test of the next iterate;
+ *   - a lane whose pair has finished swaps its state with a FRESH slot field by field (the slot becomes DONE) and goes
+ *     on with the new pair in the same trip loop; when no FRESH slot is left the next PHASE runs.
+ *
+ * Lanes of a warp are therefore at different iterations of different pairs; initialisation and epilogue still run
+ * 32 pairs at a time.  Per-pair arithmetic is the same sequence of operations as Solver::solve (bit-identical
+ * results).  Fixed-size classes only (a slot holds the whole loop-carried state: 48-74 doubles); runtime-face-count
+ * classes, the debug trace and the Jacobian kernels use pair_kernel. */
+
+template <class S>
+struct RefillLayout {
+    typedef typename S::F1 F1;
+    typedef typename S::F2 F2;
+    static constexpr int N = S::N;
+    static constexpr int X = 0;
+    static constexpr int SO1 = X + N;
+    static constexpr int ZO1 = SO1 + F1::NO;
+    static constexpr int RI1 = ZO1 + F1::NO;
+    static constexpr int SQ1 = RI1 + F1::NO;
+    static constexpr int ZQ1 = SQ1 + F1::Q;
+    static constexpr int WH1 = ZQ1 + F1::Q;
+    static constexpr int SC1 = WH1 + F1::Q; /* eta, ieta, bw */
+    static constexpr int SO2 = SC1 + (F1::Q > 0 ? 3 : 0);
+    static constexpr int ZO2 = SO2 + F2::NO;
+    static constexpr int RI2 = ZO2 + F2::NO;
+    static constexpr int SQ2 = RI2 + F2::NO;
+    static constexpr int ZQ2 = SQ2 + F2::Q;
+    static constexpr int WH2 = ZQ2 + F2::Q;
+    static constexpr int SC2 = WH2 + F2::Q;
+    static constexpr int POSE = SC2 + (F2::Q > 0 ? 3 : 0); /* Qp[9], rp[3] of the primitive that is not the frame */
+    static constexpr int SZ = POSE + 12;
+    static constexpr int META = SZ + 1; /* plan position | iteration << 32 | status << 40 */
+    static constexpr int NW = META + 1;
+    static_assert(NW >= kRecordWords + 1, "the record staging area is overlaid on the pool");
+};
+
+/* f(offset, value&, part_of_the_finished_state) over every loop-carried field of one block */
+template <class P, class F>
+__device__ __forceinline__ void visit_block(Block<P>& B, int so, int zo, int ri, int sq, int zq, int wh, int sc, F&& f)
+{
+#pragma unroll
+    for (int i = 0; i < P::NO; ++i) {
+        f(so + i, B.so[i], false);
+        f(zo + i, B.zo[i], true);
+        f(ri + i, B.rinv[i], false);
+    }
+    if (P::Q > 0) {
+#pragma unroll
+        for (int i = 0; i < P::Q; ++i) {
+            f(sq + i, B.sq[i], false);
+            f(zq + i, B.zq[i], true);
+            f(wh + i, B.wh[i], false);
+        }
+        f(sc + 0, B.eta, false);
+        f(sc + 1, B.ieta, false);
+        f(sc + 2, B.bw, false);
+    }
+}
+template <class S, class F>
+__device__ __forceinline__ void visit_state(S& sv, double& sz, F&& f)
+{
+    typedef RefillLayout<S> Lay;
+#pragma unroll
+    for (int j = 0; j < S::N; ++j) f(Lay::X + j, sv.x[j], true);
+    visit_block(sv.b1, Lay::SO1, Lay::ZO1, Lay::RI1, Lay::SQ1, Lay::ZQ1, Lay::WH1, Lay::SC1, f);
+    visit_block(sv.b2, Lay::SO2, Lay::ZO2, Lay::RI2, Lay::SQ2, Lay::ZQ2, Lay::WH2, Lay::SC2, f);
+    if constexpr (S::kFrame2) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) f(Lay::POSE + 3 * i + j, sv.p1.Qp[i][j], false);
+            f(Lay::POSE + 9 + i, sv.p1.rp[i], false);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) f(Lay::POSE + 3 * i + j, sv.p2.Qp[i][j], false);
+            f(Lay::POSE + 9 + i, sv.p2.rp[i], false);
+        }
+    }
+    f(Lay::SZ, sz, false);
+}
+
+__device__ __forceinline__ double pack_meta(int64_t pos, int it, int status)
+{
+    return __longlong_as_double((long long)(uint32_t)pos | ((long long)(it & 0xff) << 32) | ((long long)(status & 0xff) << 40));
+}
+/* position of the (r + 1)-th set bit of m (r < popc(m)) */
+__device__ __forceinline__ int nth_set_bit(unsigned m, int r)
+{
+    int base = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const unsigned lo = m & ((1u << w) - 1u);
+        const int c = __popc(lo);
+        if (r >= c) {
+            r -= c;
+            m >>= w;
+            base += w;
+        } else {
+            m = lo;
+        }
+    }
+    return base;
+}
+
+#ifndef DCOL_PHASE_ATTR
+#define DCOL_PHASE_ATTR __noinline__
+#endif
+
+/* PHASE: epilogue of the DONE slots, then initialisation of new pairs into the (then all free) slots.  Lane j works on
+ * slot j.  Precondition: no FRESH slot.  Its own function so that the trip loop's live state is saved around the call
+ * instead of competing with the initialisation for registers. */
+template <class P1, class P2>
+__device__ DCOL_PHASE_ATTR void refill_phase(const GroupArgs<P1, P2>& a, double* pool, unsigned& fresh, unsigned& done,
+                                             int64_t& next, int64_t end)
+{
+    typedef Solver<P1, P2> S;
+    typedef RefillLayout<S> Lay;
+    const int lane = threadIdx.x & 31;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool records = a.b.n_dest > 0;
+    const bool want_grad = records || (a.b.flags & DCOL_WANT_GRAD) != 0;
+    if (done) {
+        const bool mine = (done >> lane) & 1u;
+        S sv;
+        double sz_unused = 0.0;
+        long long meta = 0;
+        if (mine) {
+            visit_state(sv, sz_unused, [&](int off, double& v, bool fin) {
+                if (fin) v = pool[off * 32 + lane];
+            });
+            meta = __double_as_longlong(pool[Lay::META * 32 + lane]);
+        }
+        __syncwarp(); /* every lane has its finished state in registers: the pool may now be reused as staging */
+        const int64_t pos = (int64_t)(uint32_t)meta;
+        const int iters = (int)((meta >> 32) & 0xff), st = (int)((meta >> 40) & 0xff);
+        double* stage = pool;                                              /* [32][kRecordWords] */
+        int32_t* stage_pos = reinterpret_cast<int32_t*>(pool + 32 * kRecordWords); /* [32] */
+        if (mine) {
+            const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos] : a.b.first + pos;
+            double pose1[6], pose2[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
+                pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
+            }
+            const double alpha = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
+            if (a.b.flags & DCOL_WANT_CONTACT) {
+                double cp[3] = { nan, nan, nan };
+                if (st == DCOL_STATUS_OK) sv.contact_point(a.c1, a.c2, pose1, pose2, cp);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = cp[j]; /* proximity.py:52 */
+            }
+            double g[12];
+            if (want_grad) {
+                if (st == DCOL_STATUS_OK) {
+                    sv.gradient(a.c1, a.c2, pose1, pose2, g, !(a.b.flags & DCOL_WANT_GRAD1));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) g[j] = nan;
+                }
+            }
+            if (!records) {
+                a.b.status[k] = st;
+                a.b.iters[k] = iters;
+                a.b.alpha[k] = alpha;
+                if (want_grad) {
+                    if (a.b.flags & DCOL_WANT_GRAD1) {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) a.b.grad[6 * k + j] = g[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+                    }
+                }
+            } else {
+                double* rec = stage + lane * kRecordWords;
+                rec[0] = alpha;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) rec[1 + j] = g[j];
+                rec[13] = __longlong_as_double((long long)(uint32_t)iters | ((long long)st << 32));
+                stage_pos[lane] = (int32_t)pos;
+            }
+        }
+        if (records) {
+            /* a record is 112 contiguous bytes at its plan position: seven consecutive lanes write one record with
+             * 16-byte stores (whole sectors; full-size NVLink packets for peer / multicast destinations) */
+            __syncwarp();
+            const int64_t base = a.b.record_offset + a.b.first;
+            for (int c = lane; c < 32 * (kRecordWords / 2); c += 32) {
+                const int r = c / (kRecordWords / 2), piece = c - r * (kRecordWords / 2);
+                if (!((done >> r) & 1u)) continue;
+                const int64_t off = kRecordWords * (base + stage_pos[r]) + 2 * piece;
+                if (a.b.flags & DCOL_DEST_MULTICAST) {
+                    const float4 v = *reinterpret_cast<const float4*>(stage + r * kRecordWords + 2 * piece);
+                    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.b.dest[0] + off), "f"(v.x),
+                                 "f"(v.y), "f"(v.z), "f"(v.w)
+                                 : "memory");
+                } else {
+                    const double2 v = *reinterpret_cast<const double2*>(stage + r * kRecordWords + 2 * piece);
+                    for (int d = 0; d < a.b.n_dest; ++d) *reinterpret_cast<double2*>(a.b.dest[d] + off) = v;
+                }
+            }
+        }
+        __syncwarp();
+        done = 0;
+    }
+    /* initialisation: lane j takes plan position next + j into slot j */
+    const int64_t n_new = end - next < 32 ? end - next : 32;
+    int st = 0;
+    bool is_new = false;
+    if (lane < n_new) {
+        is_new = true;
+        const int64_t pos = next + lane;
+        const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos] : a.b.first + pos;
+        if (pos + 32 < end) { /* the pair this lane initialises in the NEXT phase: pull its poses into L2 now */
+            const int64_t kn = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos + 32] : a.b.first + pos + 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose1 + 6 * kn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose1 + 6 * kn + 5));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose2 + 6 * kn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose2 + 6 * kn + 5));
+        }
+        double pose1[6], pose2[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
+            pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
+        }
+        S sv;
+        double sz = 0.0;
+        int32_t iters = 0;
+        st = sv.init_point(a.c1, a.c2, pose1, pose2);
+        if (st == 0) st = sv.scale_and_check(a.c1, a.c2, a.b.tol, 0, iters, sz, nullptr);
+        /* park the whole state (a finished pair only needs its x and z, which are among the fields) */
+        visit_state(sv, sz, [&](int off, double& v, bool) { pool[off * 32 + lane] = v; });
+        pool[Lay::META * 32 + lane] = pack_meta(pos, iters, st == S::kContinue ? 0 : st);
+    }
+    fresh = __ballot_sync(0xffffffffu, is_new && st == S::kContinue);
+    done = __ballot_sync(0xffffffffu, is_new && st != S::kContinue);
+    next += n_new;
+    __syncwarp();
+}
+
+template <class P1, class P2>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel_refill(const __grid_constant__ GroupArgs<P1, P2> a)
+{
+    typedef Solver<P1, P2> S;
+    typedef RefillLayout<S> Lay;
+    extern __shared__ __align__(16) double pool_all[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* pool = pool_all + w * (32 * Lay::NW);
+    const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + w;
+    int64_t next = warp_id * (int64_t)a.b.per_warp;
+    if (next >= a.b.count) return;
+    const int64_t end = next + a.b.per_warp < a.b.count ? next + a.b.per_warp : a.b.count;
+    const unsigned lt = (1u << lane) - 1u;
+
+    S sv;
+    double sz = 0.0;
+    bool has = false, fin = false;
+    int it = 0, status = 0;
+    int32_t iters = 0;
+    int64_t pos = 0;
+    unsigned fresh = 0, done = 0; /* slot states, warp-uniform; a slot in neither set is free */
+
+    for (;;) {
+        /* ---- settle: finished lanes park their result, lanes without a pair take a FRESH state ---- */
+        for (;;) {
+            const unsigned m_fin = __ballot_sync(0xffffffffu, has && fin);
+            const unsigned m_empty = __ballot_sync(0xffffffffu, !has);
+            const int n_fresh = __popc(fresh), n_fin = __popc(m_fin);
+            const unsigned free_slots = ~(fresh | done);
+            const int n_free = __popc(free_slots);
+            int slot = -1, action = 0; /* 1 swap with a FRESH slot, 2 store into a free slot, 3 load a FRESH slot */
+            if (has && fin) {
+                const int r = __popc(m_fin & lt);
+                if (r < n_fresh) {
+                    slot = nth_set_bit(fresh, r);
+                    action = 1;
+                } else if (r - n_fresh < n_free) {
+                    slot = nth_set_bit(free_slots, r - n_fresh);
+                    action = 2;
+                }
+            } else if (!has) {
+                const int r = n_fin + __popc(m_empty & lt);
+                if (r < n_fresh) {
+                    slot = nth_set_bit(fresh, r);
+                    action = 3;
+                }
+            }
+            if (action == 1 || action == 3) {
+                const double my_meta = pack_meta(pos, iters, status);
+                const long long meta = __double_as_longlong(pool[Lay::META * 32 + slot]);
+                if (action == 1) {
+                    visit_state(sv, sz, [&](int off, double& v, bool part) {
+                        const double t = pool[off * 32 + slot];
+                        if (part) pool[off * 32 + slot] = v;
+                        v = t;
+                    });
+                    pool[Lay::META * 32 + slot] = my_meta;
+                } else {
+                    visit_state(sv, sz, [&](int off, double& v, bool) { v = pool[off * 32 + slot]; });
+                }
+                pos = (int64_t)(uint32_t)meta;
+                it = 0;
+                has = true;
+                fin = false;
+            } else if (action == 2) {
+                visit_state(sv, sz, [&](int off, double& v, bool part) {
+                    if (part) pool[off * 32 + slot] = v;
+                });
+                pool[Lay::META * 32 + slot] = pack_meta(pos, iters, status);
+                has = false;
+                fin = false;
+            }
+            const unsigned bit = slot >= 0 ? (1u << slot) : 0u;
+            const unsigned to_done = __reduce_or_sync(0xffffffffu, (action == 1 || action == 2) ? bit : 0u);
+            const unsigned to_free = __reduce_or_sync(0xffffffffu, action == 3 ? bit : 0u);
+            fresh &= ~(to_done | to_free);
+            done |= to_done;
+            __syncwarp();
+            const bool holder = __any_sync(0xffffffffu, has && fin);
+            if (fresh == 0 && (holder || next < end)) {
+                refill_phase<P1, P2>(a, pool, fresh, done, next, end);
+                continue; /* holders park, lanes without a pair load */
+            }
+            break;
+        }
+        if (!__any_sync(0xffffffffu, has)) { /* nothing in flight, nothing FRESH, nothing left to initialise */
+            if (done) refill_phase<P1, P2>(a, pool, fresh, done, next, end);
+            break;
+        }
+        /* ---- trip: one Newton step and the scaling / convergence test of the next iterate ---- */
+        if (has && !fin) {
+            int st = sv.newton_step(a.c1, a.c2, sz);
+            if (st != 0) {
+                fin = true;
+                status = st;
+                iters = it;
+            } else if (++it >= a.b.max_iter) {
+                fin = true;
+                status = sv.cap_status(a.b.max_iter, iters);
+            } else {
+                st = sv.scale_and_check(a.c1, a.c2, a.b.tol, it, iters, sz, nullptr);
+                if (st != S::kContinue) {
+                    fin = true;
+                    status = st;
+                }
+            }
+        }
+    }
+}
+
 /* host-side description of one launch */
 struct GroupLaunch {
     const dcol_shape* s1; /* host copies of the two shape records */
@@ -223,6 +595,32 @@ inline int resident_wave_threads()
     return sms * kMinBlocks * kThreads;
 }
 
+/* lane-refill kernels as the default path: environment DCOL_REFILL=0/1 (A/B switch), else DCOL_REFILL_DEFAULT */
+#ifndef DCOL_REFILL_DEFAULT
+#define DCOL_REFILL_DEFAULT 0
+#endif
+inline bool refill_enabled()
+{
+    static const int on = getenv("DCOL_REFILL") ? atoi(getenv("DCOL_REFILL")) : DCOL_REFILL_DEFAULT;
+    return on != 0;
+}
+/* plan positions per warp: 32 x generations.  More generations amortise the fill and the ragged drain of a warp's
+ * chunk; fewer give the grid more warps to balance.  Small groups degenerate to one generation (one pair per lane). */
+inline int32_t refill_pairs_per_warp(int64_t count)
+{
+    static const int forced = getenv("DCOL_REFILL_GEN") ? atoi(getenv("DCOL_REFILL_GEN")) : 0;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+    }
+    int64_t gen = forced > 0 ? forced : count / (32LL * sms * kMinBlocks * (kThreads / 32));
+    gen = gen < 1 ? 1 : (gen > 16 ? 16 : gen);
+    if (forced > 0) gen = forced;
+    return (int32_t)(32 * gen);
+}
+
 template <int C1, int C2, bool JAC = false>
 cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
 {
@@ -233,6 +631,17 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
     fill_const(*g.s2, g.A, g.b, a.c2);
     a.b = g.args;
     if (g.args.count <= 0) return cudaSuccess;
+    if constexpr (!JAC && !P1::dyn && !P2::dyn) {
+        if (!g.args.trace && !(g.args.flags & DCOL_ONE_PAIR_PER_THREAD) && ((g.args.flags & DCOL_LANE_REFILL) || refill_enabled())) {
+            typedef RefillLayout<Solver<P1, P2>> Lay;
+            a.b.per_warp = refill_pairs_per_warp(g.args.count);
+            const int64_t warps = (g.args.count + a.b.per_warp - 1) / a.b.per_warp;
+            const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
+            const size_t smem = sizeof(double) * (kThreads / 32) * 32 * Lay::NW;
+            pair_kernel_refill<P1, P2><<<(unsigned)blocks, kThreads, smem, stream>>>(a);
+            return cudaGetLastError();
+        }
+    }
     a.b.ahead = g.args.trace ? 0 : resident_wave_threads();
     const int64_t blocks = (g.args.count + kThreads - 1) / kThreads;
     pair_kernel<P1, P2, JAC><<<(unsigned)blocks, kThreads, g.args.n_dest > 0 ? kStageBytes : 0, stream>>>(a);

@@ -1008,9 +1008,13 @@ struct Solver {
         dcm_derivative_contract(pm, Qm, Mq, g6 + 3);
     }
 
-    /* ---- the whole solve.  pose = (r, p).  Returns the status word; fills res. */
-    DCOL_HD int solve(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double tol, int max_iter,
-                      bool want_grad, PairResult<N>& res, const Trace* trace)
+    /* ---- the solve in three pieces: solve() below runs them in sequence; the lane-refill kernel (dcol_kernels.cuh)
+     * runs init_point for 32 new pairs at a time and scale_and_check / newton_step in lanes that are at different
+     * iterations of different pairs.  Same operations in the same order either way. */
+    static constexpr int kContinue = -1;
+
+    /* pose = (r, p) -> working frame and the initial point of pdip.py:291-332.  Returns 0 or a failure status. */
+    DCOL_HD int init_point(const C1& c1, const C2& c2, const double* pose1, const double* pose2)
     {
         {
             double Q1[3][3], Q2[3][3];
@@ -1022,113 +1026,146 @@ struct Solver {
             w2.set_pose(c2, pose2, Q2);
             set_relative(w1, w2);
         }
-        res.iters = 0;
-
         double L[N][N], Li[N];
-        /* -------- initial point, pdip.py:291-332 -------- */
-        {
-            double M[N][N], gth[N];
+        double M[N][N], gth[N];
+        DCOL_UNROLL
+        for (int i = 0; i < N; ++i) {
+            gth[i] = 0.0;
             DCOL_UNROLL
-            for (int i = 0; i < N; ++i) {
-                gth[i] = 0.0;
-                DCOL_UNROLL
-                for (int j = 0; j < N; ++j) M[i][j] = 0.0;
-            }
-            init_accumulate<F1>(p1, c1, CE1, M, gth);
-            init_accumulate<F2>(p2, c2, CE2, M, gth);
-            if (int bad = chol(M, L, Li)) return res.status = bad; /* numpy cholesky -> LinAlgError; check_finite */
-            DCOL_UNROLL
-            for (int j = 0; j < N; ++j) x[j] = gth[j];
-            chol_solve(L, Li, x); /* x_hat = (G^T G)^-1 G^T h */
-            if (probe_vec(x) != 0.0) return res.status = DCOL_STATUS_NON_FINITE;
-            rows<F1, true>(p1, c1, CE1, x, b1.so, b1.sq);
-            rows<F2, true>(p2, c2, CE2, x, b2.so, b2.sq); /* s~ = G x_hat - h */
-            /* solve_triangular(F, -c) reads the UPPER triangle of the lower factor, i.e. its diagonal
-             * (pdip.py:326); then a proper back substitution with F^T */
-            double xd[N];
-            DCOL_UNROLL
-            for (int i = 0; i < N; ++i) xd[i] = (i == 3) ? -Li[3] : 0.0;
-            DCOL_UNROLL
-            for (int i = N - 1; i >= 0; --i) {
-                double t = xd[i];
-                DCOL_UNROLL
-                for (int k = i + 1; k < N; ++k) t -= L[k][i] * xd[k];
-                xd[i] = t * Li[i];
-            }
-            rows<F1, false>(p1, c1, CE1, xd, b1.zo, b1.zq);
-            rows<F2, false>(p2, c2, CE2, xd, b2.zo, b2.zq); /* z~ = G x */
-            bring2cone<0>(c1, c2);
-            bring2cone<1>(c1, c2);
+            for (int j = 0; j < N; ++j) M[i][j] = 0.0;
         }
+        init_accumulate<F1>(p1, c1, CE1, M, gth);
+        init_accumulate<F2>(p2, c2, CE2, M, gth);
+        if (int bad = chol(M, L, Li)) return bad; /* numpy cholesky -> LinAlgError; check_finite */
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) x[j] = gth[j];
+        chol_solve(L, Li, x); /* x_hat = (G^T G)^-1 G^T h */
+        if (probe_vec(x) != 0.0) return DCOL_STATUS_NON_FINITE;
+        rows<F1, true>(p1, c1, CE1, x, b1.so, b1.sq);
+        rows<F2, true>(p2, c2, CE2, x, b2.so, b2.sq); /* s~ = G x_hat - h */
+        /* solve_triangular(F, -c) reads the UPPER triangle of the lower factor, i.e. its diagonal
+         * (pdip.py:326); then a proper back substitution with F^T */
+        double xd[N];
+        DCOL_UNROLL
+        for (int i = 0; i < N; ++i) xd[i] = (i == 3) ? -Li[3] : 0.0;
+        DCOL_UNROLL
+        for (int i = N - 1; i >= 0; --i) {
+            double t = xd[i];
+            DCOL_UNROLL
+            for (int k = i + 1; k < N; ++k) t -= L[k][i] * xd[k];
+            xd[i] = t * Li[i];
+        }
+        rows<F1, false>(p1, c1, CE1, xd, b1.zo, b1.zq);
+        rows<F2, false>(p2, c2, CE2, xd, b2.zo, b2.zq); /* z~ = G x */
+        bring2cone<0>(c1, c2);
+        bring2cone<1>(c1, c2);
+        return 0;
+    }
 
+    /* top of iteration `it` (pdip.py:396-422): NT scaling of the current iterate, sz = s'z, the finiteness checks and
+     * the only convergence test, mu < tol.  Returns kContinue, DCOL_STATUS_OK (converged) or a failure status;
+     * `iters` is what the batch API reports for that outcome. */
+    DCOL_HD int scale_and_check(const C1& c1, const C2& c2, double tol, int it, int32_t& iters, double& sz,
+                                const Trace* trace)
+    {
+        iters = it;
+        double bad = 0.0;
+        sz = nt_and_mu<F1>(c1, b1, bad);
+        sz += nt_and_mu<F2>(c2, b2, bad);
+        if (nonfinite_probe(sz) != 0.0) {
+            /* the previous step left a non-finite iterate: the reference's check_finite raised inside it */
+            iters = it > 0 ? it - 1 : 0;
+            return DCOL_STATUS_NON_FINITE;
+        }
+        if (bad != 0.0) return DCOL_STATUS_NON_FINITE; /* cho_factor(W_soc) check_finite */
+        const double mu = sz * ideg_of(c1, c2);
+        if (trace && trace->mu) trace->mu[it] = mu;
+        if (mu < tol) return DCOL_STATUS_OK; /* the only convergence test, pdip.py:418-422 */
+        return kContinue;
+    }
+
+    DCOL_HD static double ideg_of(const C1& c1, const C2& c2)
+    {
         const int deg = P1::n_ort(c1) + P2::n_ort(c2) + (P1::Q > 0) + (P2::Q > 0);
-        const double ideg = 1.0 / (double)deg;
+        return 1.0 / (double)deg;
+    }
 
+    /* one predictor-corrector step from the scaled iterate (pdip.py:424-466).  Returns 0 or a failure status. */
+    DCOL_HD int newton_step(const C1& c1, const C2& c2, double sz)
+    {
+        const double mu = sz * ideg_of(c1, c2);
+        double L[N][N], Li[N];
+        double M[N][N], va[N], vl[N];
+        DCOL_UNROLL
+        for (int i = 0; i < N; ++i) {
+            va[i] = (i == 3) ? -1.0 : 0.0; /* -c; pass_a adds -G^T W^-2 rz */
+            vl[i] = 0.0;
+            DCOL_UNROLL
+            for (int j = 0; j < N; ++j) M[i][j] = 0.0;
+        }
+        pass_a<F1>(p1, c1, CE1, b1, x, M, va, vl);
+        pass_a<F2>(p2, c2, CE2, b2, x, M, va, vl);
+        double dx[N];
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) dx[j] = va[j]; /* bx + G~^T b~ */
+        if (int bad = chol(M, L, Li)) return bad; /* scipy cholesky: check_finite, LinAlgError */
+        chol_solve(L, Li, dx);
+
+        /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
+        double tm[2] = { 0.0, 0.0 }, d_sz = 0.0, vk[N];
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) vk[j] = 0.0;
+        pass_b<F1>(p1, c1, CE1, b1, dx, tm, d_sz, vk);
+        pass_b<F2>(p2, c2, CE2, b2, dx, tm, d_sz, vk);
+        double t = max_(tm[0], tm[1]);
+        double a = t > 1.0 ? rcp_(t) : 1.0;
+        /* (s + a ds)'(z + a dz) / s'z with ds~ + dz~ = -lambda for the affine direction: 1 - a + a^2 <ds~, dz~> / s'z */
+        const double rho = (1.0 - a) + (a * a) * (d_sz * rcp_(sz));
+        const double cl = max_(0.0, min_(1.0, rho));
+        const double sigmu = (cl * cl * cl) * mu;
+
+        /* corrector: rhs = rhs_affine + G~^T k - sigma mu G~^T (lambda^-1 o e), same factor   pdip.py:450-460 */
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) dx[j] = va[j] + vk[j] - sigmu * vl[j];
+        chol_solve(L, Li, dx);
+        tm[0] = 0.0;
+        tm[1] = 0.0;
+        pass_c<F1>(p1, c1, CE1, b1, dx, sigmu, tm);
+        pass_c<F2>(p2, c2, CE2, b2, dx, sigmu, tm);
+        t = max_(tm[0], tm[1]);
+        a = min_(1.0, 0.99 * (t > 1.0 ? rcp_(t) : 1.0)); /* pdip.py:462 */
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) x[j] += a * dx[j];
+        pass_d<F1>(c1, b1, a);
+        pass_d<F2>(c2, b2, a);
+        return 0;
+    }
+
+    /* what the reference reports when the iteration cap is reached (pdip.py:470), or when the last step itself went
+     * non-finite */
+    DCOL_HD int cap_status(int max_iter, int32_t& iters) const
+    {
+        iters = max_iter;
+        if (probe_vec(x) != 0.0) {
+            iters = max_iter - 1;
+            return DCOL_STATUS_NON_FINITE;
+        }
+        return DCOL_STATUS_MAX_ITER;
+    }
+
+    /* ---- the whole solve.  pose = (r, p).  Returns the status word; fills res. */
+    DCOL_HD int solve(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double tol, int max_iter,
+                      bool want_grad, PairResult<N>& res, const Trace* trace)
+    {
+        res.iters = 0;
+        if (int bad = init_point(c1, c2, pose1, pose2)) return res.status = bad;
         for (int it = 0; it < max_iter; ++it) {
-            res.iters = it;
-            double bad = 0.0;
-            double sz = nt_and_mu<F1>(c1, b1, bad);
-            sz += nt_and_mu<F2>(c2, b2, bad);
-            if (nonfinite_probe(sz) != 0.0) {
-                /* the previous step left a non-finite iterate: the reference's check_finite raised inside it */
-                res.iters = it > 0 ? it - 1 : 0;
-                return res.status = DCOL_STATUS_NON_FINITE;
-            }
-            if (bad != 0.0) return res.status = DCOL_STATUS_NON_FINITE; /* cho_factor(W_soc) check_finite */
-            const double mu = sz * ideg;
-            if (trace && trace->mu) trace->mu[it] = mu;
-            if (mu < tol) return res.status = DCOL_STATUS_OK; /* the only convergence test, pdip.py:418-422 */
-
-            double M[N][N], va[N], vl[N];
-            DCOL_UNROLL
-            for (int i = 0; i < N; ++i) {
-                va[i] = (i == 3) ? -1.0 : 0.0; /* -c; pass_a adds -G^T W^-2 rz */
-                vl[i] = 0.0;
-                DCOL_UNROLL
-                for (int j = 0; j < N; ++j) M[i][j] = 0.0;
-            }
-            pass_a<F1>(p1, c1, CE1, b1, x, M, va, vl);
-            pass_a<F2>(p2, c2, CE2, b2, x, M, va, vl);
-            double dx[N];
-            DCOL_UNROLL
-            for (int j = 0; j < N; ++j) dx[j] = va[j]; /* bx + G~^T b~ */
-            if (int bad = chol(M, L, Li)) return res.status = bad; /* scipy cholesky: check_finite, LinAlgError */
-            chol_solve(L, Li, dx);
-
-            /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
-            double tm[2] = { 0.0, 0.0 }, d_sz = 0.0, vk[N];
-            DCOL_UNROLL
-            for (int j = 0; j < N; ++j) vk[j] = 0.0;
-            pass_b<F1>(p1, c1, CE1, b1, dx, tm, d_sz, vk);
-            pass_b<F2>(p2, c2, CE2, b2, dx, tm, d_sz, vk);
-            double t = max_(tm[0], tm[1]);
-            double a = t > 1.0 ? rcp_(t) : 1.0;
-            /* (s + a ds)'(z + a dz) / s'z with ds~ + dz~ = -lambda for the affine direction: 1 - a + a^2 <ds~, dz~> / s'z */
-            const double rho = (1.0 - a) + (a * a) * (d_sz * rcp_(sz));
-            const double cl = max_(0.0, min_(1.0, rho));
-            const double sigmu = (cl * cl * cl) * mu;
-
-            /* corrector: rhs = rhs_affine + G~^T k - sigma mu G~^T (lambda^-1 o e), same factor   pdip.py:450-460 */
-            DCOL_UNROLL
-            for (int j = 0; j < N; ++j) dx[j] = va[j] + vk[j] - sigmu * vl[j];
-            chol_solve(L, Li, dx);
-            tm[0] = 0.0;
-            tm[1] = 0.0;
-            pass_c<F1>(p1, c1, CE1, b1, dx, sigmu, tm);
-            pass_c<F2>(p2, c2, CE2, b2, dx, sigmu, tm);
-            t = max_(tm[0], tm[1]);
-            a = min_(1.0, 0.99 * (t > 1.0 ? rcp_(t) : 1.0)); /* pdip.py:462 */
-            DCOL_UNROLL
-            for (int j = 0; j < N; ++j) x[j] += a * dx[j];
-            pass_d<F1>(c1, b1, a);
-            pass_d<F2>(c2, b2, a);
+            double sz;
+            const int st = scale_and_check(c1, c2, tol, it, res.iters, sz, trace);
+            if (st != kContinue) return res.status = st;
+            if (int bad = newton_step(c1, c2, sz)) return res.status = bad;
         }
-        res.iters = max_iter;
-        if (probe_vec(x) != 0.0) { /* the last step itself went non-finite */
-            res.iters = max_iter - 1;
-            return res.status = DCOL_STATUS_NON_FINITE;
-        }
-        return res.status = DCOL_STATUS_MAX_ITER; /* pdip.py:470 */
+        return res.status = cap_status(max_iter, res.iters);
     }
 
     template <int SEL>
@@ -1195,7 +1232,9 @@ struct Solver {
         for (int i = 0; i < 3; ++i) out[i] = wf.rp[i] + (wf.Qp[i][0] * x[0] + wf.Qp[i][1] * x[1] + wf.Qp[i][2] * x[2]);
     }
 
-    DCOL_HD void gradient(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double* grad) const
+    /* second = false: only grad[0:6] = d alpha / d [r1 p1] is filled (DCOL_WANT_GRAD1) */
+    DCOL_HD void gradient(const C1& c1, const C2& c2, const double* pose1, const double* pose2, double* grad,
+                          bool second = true) const
     {
         double Q1[3][3], Q2[3][3], xw[N];
         P1 w1;
@@ -1203,7 +1242,7 @@ struct Solver {
         world_frames(c1, c2, pose1, pose2, w1, w2, Q1, Q2, xw);
         const double (&Rf)[3][3] = kFrame2 ? w2.Qp : w1.Qp;
         grad_block<P1>(w1, c1, CE1, b1, xw, Rf, pose1 + 3, Q1, grad);
-        grad_block<P2>(w2, c2, CE2, b2, xw, Rf, pose2 + 3, Q2, grad + 6);
+        if (second) grad_block<P2>(w2, c2, CE2, b2, xw, Rf, pose2 + 3, Q2, grad + 6);
     }
 
     /* ------------------------------------------------------------------------------------------------

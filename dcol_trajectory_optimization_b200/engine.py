@@ -24,6 +24,7 @@ from .shapes import (STATUS_MAX_ITER, STATUS_NON_FINITE, STATUS_NOT_PD, STATUS_O
                      pose_of)
 
 WANT_CONTACT, WANT_GRAD, FIX_CASE4 = _lib.WANT_CONTACT, _lib.WANT_GRAD, _lib.FIX_CASE4
+ONE_PAIR_PER_THREAD, WANT_GRAD1, LANE_REFILL = _lib.ONE_PAIR_PER_THREAD, _lib.WANT_GRAD1, _lib.LANE_REFILL
 
 
 def raise_for_status(status: int):
@@ -189,16 +190,21 @@ class ProximityEngine:
 
     def solve(self, plan: Plan, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
               want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False,
-              want_jac: bool = False) -> BatchResult:
+              want_jac: bool = False, grad1: bool = False, one_pair_per_thread: bool = False,
+              lane_refill: bool = False) -> BatchResult:
         """Enqueue the solve of every pair of ``plan`` on the current CUDA stream.
 
         ``pose1``/``pose2``: float64 CUDA tensors ``[B, 6]`` (rows ``r, p``).  Returns CUDA tensors;
         the call does not synchronise.  ``want_jac`` (extension) also returns the
         solution Jacobian ``jac[B, 4, 12]`` = d(contact point, alpha) / d[r1 p1 r2 p2], computed inside the solve
         kernel by an adjoint solve with the factor of the final reduced KKT matrix
-        (``dcol_proximity_batch_jacobian``)."""
+        (``dcol_proximity_batch_jacobian``).  ``grad1``: the gradient is ``[B, 6]``, d alpha / d[r1 p1] only
+        (``DCOL_WANT_GRAD1``: what the reference's callers consume).  ``one_pair_per_thread``: use the kernels
+        without lane refill, ``lane_refill``: force the lane-refill kernels (neither: the library's default)."""
         import torch
         B = plan.size
+        if grad1 and want_jac:
+            raise ValueError("grad1 is not available together with want_jac")
         for name, t in (("pose1", pose1), ("pose2", pose2)):
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (B, 6)):
                 raise ValueError(f"{name} must be a contiguous float64 CUDA tensor of shape ({B}, 6)")
@@ -207,12 +213,15 @@ class ProximityEngine:
             out = BatchResult(
                 alpha=torch.empty(B, dtype=torch.float64, device=dev),
                 contact=torch.empty((B, 3), dtype=torch.float64, device=dev) if want_contact else None,
-                grad=torch.empty((B, 12), dtype=torch.float64, device=dev) if want_grad else None,
+                grad=torch.empty((B, 6 if grad1 else 12), dtype=torch.float64, device=dev) if want_grad else None,
                 iters=torch.empty(B, dtype=torch.int32, device=dev),
                 status=torch.empty(B, dtype=torch.int32, device=dev),
                 jac=torch.empty((B, 4, 12), dtype=torch.float64, device=dev) if want_jac else None)
+        if out.grad is not None and tuple(out.grad.shape) != (B, 6 if grad1 else 12):
+            raise ValueError(f"out.grad must have shape ({B}, {6 if grad1 else 12})")
         flags = ((WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
-                 | (FIX_CASE4 if fix_case4 else 0))
+                 | (FIX_CASE4 if fix_case4 else 0) | (WANT_GRAD1 if (grad1 and out.grad is not None) else 0)
+                 | (ONE_PAIR_PER_THREAD if one_pair_per_thread else 0) | (LANE_REFILL if lane_refill else 0))
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if want_jac:
             if out.jac is None:
@@ -230,7 +239,8 @@ class ProximityEngine:
         return out
 
     def solve_records(self, plan: Plan, pose1, pose2, dest_ptrs, record_offset: int = 0, tol: float = 1e-6,
-                      max_iter: int = 50, contact=None, fix_case4: bool = False, multicast: bool = False):
+                      max_iter: int = 50, contact=None, fix_case4: bool = False, multicast: bool = False,
+                      one_pair_per_thread: bool = False, lane_refill: bool = False):
         """Record mode: every pair's 112-byte record ``{alpha, grad[12], iters, status}`` is written, in plan
         order, to each of the raw device addresses ``dest_ptrs`` (local buffers or peer-GPU buffers mapped with
         CUDA IPC — the all-gather of the results fused into the solve).  Enqueues on the current stream."""
@@ -243,13 +253,16 @@ class ProximityEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_lib.lib().dcol_proximity_batch_records(
             plan._handle, pose1.data_ptr(), pose2.data_ptr(), float(tol), int(max_iter),
-            (FIX_CASE4 if fix_case4 else 0) | (_lib.DEST_MULTICAST if multicast else 0), len(dest_ptrs), arr,
+            (FIX_CASE4 if fix_case4 else 0) | (_lib.DEST_MULTICAST if multicast else 0)
+            | (ONE_PAIR_PER_THREAD if one_pair_per_thread else 0) | (LANE_REFILL if lane_refill else 0), len(dest_ptrs), arr,
             int(record_offset), contact.data_ptr() if contact is not None else None, stream))
 
     # ------------------------------------------------------------------ host buffers
     def solve_host(self, idx1, idx2, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
-                   want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False) -> BatchResult:
-        """The reference-facing call: NumPy buffers in, NumPy buffers out, copies inside."""
+                   want_contact: bool = True, out: BatchResult | None = None, fix_case4: bool = False,
+                   grad1: bool = False, one_pair_per_thread: bool = False) -> BatchResult:
+        """The reference-facing call: NumPy buffers in, NumPy buffers out, copies inside.  ``grad1``: ``grad`` is
+        ``[B, 6]`` (d alpha / d[r1 p1], ``DCOL_WANT_GRAD1``), which halves the bytes that come back over PCIe."""
         idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
         idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
         pose1 = np.ascontiguousarray(pose1, dtype=np.float64).reshape(-1, 6)
@@ -259,10 +272,13 @@ class ProximityEngine:
             raise ValueError("idx1, idx2, pose1, pose2 must describe the same number of pairs")
         if out is None:
             out = BatchResult(alpha=np.empty(B), contact=np.empty((B, 3)) if want_contact else None,
-                              grad=np.empty((B, 12)) if want_grad else None, iters=np.empty(B, np.int32),
+                              grad=np.empty((B, 6 if grad1 else 12)) if want_grad else None, iters=np.empty(B, np.int32),
                               status=np.empty(B, np.int32))
+        if out.grad is not None and tuple(out.grad.shape) != (B, 6 if grad1 else 12):
+            raise ValueError(f"out.grad must have shape ({B}, {6 if grad1 else 12})")
         flags = ((WANT_CONTACT if out.contact is not None else 0) | (WANT_GRAD if out.grad is not None else 0)
-                 | (FIX_CASE4 if fix_case4 else 0))
+                 | (FIX_CASE4 if fix_case4 else 0) | (WANT_GRAD1 if (grad1 and out.grad is not None) else 0)
+                 | (ONE_PAIR_PER_THREAD if one_pair_per_thread else 0))
         _lib.check(_lib.lib().dcol_proximity_batch_host(
             self._table, idx1.ctypes.data, idx2.ctypes.data, pose1.ctypes.data, pose2.ctypes.data, B, float(tol),
             int(max_iter), flags, out.alpha.ctypes.data, out.contact.ctypes.data if out.contact is not None else None,

@@ -133,16 +133,62 @@ class GatherPipeline:
         return [packed_views(g[rank], hi - lo) for g, (lo, hi) in zip(self.gathered, self.bounds)]
 
 
-class PeerRecordGather:
+class _RecordGather:
+    """Shared behaviour of the two fused-gather fabrics.
+
+    DOUBLE BUFFERED: the gathered allocation holds two halves ``[2, world, B, 14]`` and consecutive steps alternate
+    between them.  With a single buffer, rank A's kernel of step n+1 (free to start as soon as A's own handshake n
+    has completed) could store into slot A of rank B's buffer while B is still reading step n.  With two halves the
+    buffer that step n+2 overwrites is the one step n was read from, and A cannot start step n+2 before handshake
+    n+1 has completed on A, which needs B's stream to have reached its handshake n+1 — stream-ordered after B's reads
+    of step n.  So: results of a step stay valid until the step after next is enqueued, provided every consumer reads
+    them on the stream the steps are enqueued on (as :class:`FusedShardedSolver` does), and no extra synchronisation
+    is needed.
+
+    Use: ``ptrs = g.begin_step()`` -> ``engine.solve_records(..., ptrs, multicast=g.multicast)`` -> ``g.handshake()``
+    -> read ``g.gathered`` (``[world, B, 14]`` float64, plan order per source rank)."""
+
+    multicast = False
+
+    def _init_common(self, B, rank, world, local_device, group):
+        self.B, self.rank, self.world, self.dev, self.group = B, rank, world, local_device, group
+        self._half = 1          # begin_step() flips first: step 0 uses half 0
+        self._flag = torch.zeros(1, dtype=torch.float32, device=torch.device("cuda", local_device))
+
+    @property
+    def half_words(self) -> int:
+        from . import _lib
+        return self.world * max(self.B, 1) * _lib.RECORD_WORDS
+
+    def begin_step(self):
+        """Switch to the other half and return the destination addresses the solve of this step must write to."""
+        self._half ^= 1
+        return self.dest_ptrs
+
+    @property
+    def dest_ptrs(self):
+        from . import _lib
+        slot = (self._half * self.half_words + self.rank * max(self.B, 1) * _lib.RECORD_WORDS) * 8
+        return [base + slot for base in self._dest_bases]
+
+    @property
+    def gathered(self):
+        """``[world, B, 14]`` view of the half the current step writes / wrote."""
+        return self._both[self._half][:, :self.B]
+
+    def handshake(self):
+        """Stream-ordered completion barrier (4-byte all-reduce): when it has completed on this rank's stream every
+        peer's kernel of this step, and with it every peer's stores into this rank's buffer, has completed."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, group=self.group)
+
+
+class PeerRecordGather(_RecordGather):
     """The all-gather fused into the solve: every rank's kernel writes its 112-byte records straight into
     slot ``rank`` of EVERY rank's gathered buffer, locally and over NVLink peer mappings (CUDA IPC), from
     the kernel's epilogue.  Nothing is packed, copied or sent afterwards; a scalar all-reduce on the same
-    stream is the completion handshake (when it returns on a rank's stream, every peer's kernel — and with
-    it every peer's stores into this rank's buffer — has completed).
-
-    ``gathered``: this rank's ``[world, B, 14]`` float64 tensor (plan order per source rank; use
-    ``engine.records_to_result(gathered[r], perm_r)`` for pair order).  All ranks must use the same ``B``.
-    """
+    stream is the completion handshake.  All ranks must use the same ``B``.  See :class:`_RecordGather`."""
 
     multicast = False
 
@@ -154,13 +200,12 @@ class PeerRecordGather:
         if world > _lib.MAX_DEST:
             raise ValueError(f"at most {_lib.MAX_DEST} ranks per node")
         L = _lib.lib()
-        self.B, self.rank, self.world, self.dev, self.group = B, rank, world, local_device, group
-        nbytes = world * B * _lib.RECORD_WORDS * 8
+        self._init_common(B, rank, world, local_device, group)
+        nbytes = 2 * self.half_words * 8
         ptr = C.c_void_p()
         _lib.check(L.dcol_device_alloc(local_device, nbytes, C.byref(ptr)))
         self._ptr = ptr.value
-        self.gathered = device_view(self._ptr, (world, max(B, 1), _lib.RECORD_WORDS), torch.device("cuda", local_device))
-        self.gathered = self.gathered[:, :B]
+        self._both = device_view(self._ptr, (2, world, max(B, 1), _lib.RECORD_WORDS), torch.device("cuda", local_device))
         handle = (C.c_ubyte * 64)()
         self._peers = {}
         if world > 1:
@@ -175,15 +220,7 @@ class PeerRecordGather:
                 buf = (C.c_ubyte * 64).from_buffer_copy(h)
                 _lib.check(L.dcol_ipc_import(local_device, C.cast(buf, C.c_void_p), C.byref(p)))
                 self._peers[r] = p.value
-        slot = B * _lib.RECORD_WORDS * 8 * rank      # this rank's slot inside every destination buffer
-        self.dest_ptrs = [(self._ptr if r == rank else self._peers[r]) + slot for r in range(world)]
-        self._flag = torch.zeros(1, dtype=torch.float32, device=torch.device("cuda", local_device))
-
-    def handshake(self):
-        """Stream-ordered completion barrier (4-byte all-reduce)."""
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._flag, group=self.group)
+        self._dest_bases = [(self._ptr if r == rank else self._peers[r]) for r in range(world)]
 
     def close(self):
         from . import _lib
@@ -196,7 +233,7 @@ class PeerRecordGather:
             self._ptr = None
 
 
-class MulticastRecordGather:
+class MulticastRecordGather(_RecordGather):
     """The fused all-gather over NVLink SHARP: the gathered buffers of all ranks are one symmetric allocation
     (``torch.distributed._symmetric_memory``) with a MULTICAST address, and the solve kernel's epilogue issues one
     ``multimem.st`` per 16 bytes of a record; the NVSwitch replicates it into slot ``rank`` of every rank's
@@ -209,26 +246,21 @@ class MulticastRecordGather:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        self.B, self.rank, self.world, self.dev, self.group = B, rank, world, local_device, group
+        self._init_common(B, rank, world, local_device, group)
         dev = torch.device("cuda", local_device)
-        flat = symm_mem.empty(world * max(B, 1) * _lib.RECORD_WORDS, dtype=torch.float64, device=dev)
+        flat = symm_mem.empty(2 * self.half_words, dtype=torch.float64, device=dev)
         self._hdl = symm_mem.rendezvous(flat, group if group is not None else dist.group.WORLD)
         mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
         if mc == 0:
             raise RuntimeError("symmetric memory has no multicast address on this fabric")
         self._flat = flat
-        self.gathered = flat.view(world, max(B, 1), _lib.RECORD_WORDS)[:, :B]
-        self.dest_ptrs = [mc + B * _lib.RECORD_WORDS * 8 * rank]
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-
-    def handshake(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._flag, group=self.group)
+        self._both = flat.view(2, world, max(B, 1), _lib.RECORD_WORDS)
+        self._dest_bases = [mc]
 
     def close(self):
         self._hdl = None
         self._flat = None
+        self._both = None
 
 
 class FusedShardedSolver:
@@ -245,6 +277,8 @@ class FusedShardedSolver:
         self.engine, self.rank, self.world, self.group = engine, rank, world, group
         idx1, idx2 = torch.as_tensor(idx1), torch.as_tensor(idx2)
         self.B = int(idx1.shape[0])
+        if self.B < world:      # the same on every rank, so every rank raises (no rank is left waiting in a collective)
+            raise ValueError(f"FusedShardedSolver needs at least one pair per rank (B = {self.B}, world = {world})")
         self.bounds = [shard_bounds(self.B, r, world) for r in range(world)]
         self.Bmax = max(hi - lo for lo, hi in self.bounds)
         lo, hi = self.bounds[rank]
@@ -288,7 +322,8 @@ class FusedShardedSolver:
         p1 = pose1.index_select(0, self._sel).contiguous()
         p2 = pose2.index_select(0, self._sel).contiguous()
         if self.world > 1:
-            self.engine.solve_records(self.plan, p1, p2, self.gather.dest_ptrs, tol=tol, max_iter=max_iter,
+            # double-buffered gathered slots: see _RecordGather (back-to-back solves may overlap across ranks)
+            self.engine.solve_records(self.plan, p1, p2, self.gather.begin_step(), tol=tol, max_iter=max_iter,
                                       multicast=self.gather.multicast)
             self.gather.handshake()
             rec = self.gather.gathered.reshape(self.world * self.Bmax, WORDS_PER_PAIR)

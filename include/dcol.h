@@ -78,11 +78,21 @@ enum {
     DCOL_WANT_GRAD    = 2u, /* d alpha / d [r1 p1 r2 p2], proximity_gradient.py:71-77 layout  */
     DCOL_DEST_MULTICAST = 8u, /* dcol_proximity_batch_records only: dest[0] is an NVLink multicast address (NVLS);
                                  every record leaves as multimem.st and the switch delivers it to all ranks' buffers */
-    DCOL_FIX_CASE4    = 4u  /* EXTENSION: also solve the pairs in which both primitives carry extra variables
+    DCOL_FIX_CASE4    = 4u, /* EXTENSION: also solve the pairs in which both primitives carry extra variables
                                (capsule / cylinder / polygon squared), with the column layout
                                [x, alpha, extras1, extras2] that combine_problem_matrices.py:58-67 builds for the
                                second primitive but forgets to pad the first to; without this flag those pairs
                                report DCOL_STATUS_UNSUPPORTED, as the reference raises ValueError */
+    DCOL_ONE_PAIR_PER_THREAD = 16u, /* force the kernels in which a thread owns one pair from start to finish ...      */
+    DCOL_LANE_REFILL  = 64u, /* ... or the lane-refill kernels (a warp owns a chunk of pairs; a lane whose pair has
+                               converged takes the next pre-initialised pair from a shared-memory pool).  Neither
+                               flag: the library's default (environment DCOL_REFILL=0/1 overrides it).  Same per-pair
+                               operations either way; results agree to rounding (different kernels, different
+                               fused-multiply-add contraction), with identical iteration counts and status words */
+    DCOL_WANT_GRAD1   = 32u /* with DCOL_WANT_GRAD: grad is [B][6], only d alpha / d [r1 p1] — the half every caller of
+                               the reference consumes (systems/piano_mover.py:94,
+                               cluttered_hallway_quadrotor.py:161-163 use g[0:6] and drop g[6:12]); halves the
+                               device->host bytes of the host entry points */
 };
 
 /* One primitive SHAPE (no pose).  144 bytes, natural alignment. */
@@ -135,7 +145,7 @@ int dcol_plan_refine(dcol_plan* plan, const int32_t* d_iters, void* stream);
  *   pose1, pose2 : [B][6] rows (r, p)
  *   alpha        : [B]
  *   contact      : [B][3]   or NULL unless DCOL_WANT_CONTACT
- *   grad         : [B][12]  or NULL unless DCOL_WANT_GRAD
+ *   grad         : [B][12]  or NULL unless DCOL_WANT_GRAD ([B][6] with DCOL_WANT_GRAD1)
  *   iters,status : [B] int32 (PDIP iterations taken; DCOL_STATUS_*)
  * tol is the reference's pdip_tol (1e-6 at both call sites); max_iter must be in 1..DCOL_MAX_ITER
  * (the reference always runs with 50). */

@@ -36,10 +36,10 @@ def main():
             return
     else:
         pg = parallel.PeerRecordGather(B, rank, world, local)
-    pg.gathered.fill_(-1.0)
+    pg._both.fill_(-1.0)
     dist.barrier()
     torch.cuda.synchronize()
-    eng.solve_records(plan, d1, d2, pg.dest_ptrs, multicast=pg.multicast)
+    eng.solve_records(plan, d1, d2, pg.begin_step(), multicast=pg.multicast)
     pg.handshake()
     torch.cuda.synchronize()
     # every rank's perm differs: exchange them once (static per plan)
@@ -64,6 +64,30 @@ def main():
     torch.cuda.synchronize()
     assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status)
     assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad)
+    # back-to-back solves with drifting poses, nothing synchronised in between, and one rank's CONSUMER delayed after
+    # every handshake (its reads of step n are still pending while the other rank is already storing step n+1): with a
+    # single gathered buffer this returns records of the wrong step (write-after-read); the double buffer must not
+    n_steps = 60
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)                       # same drift on every rank
+    base1, base2 = torch.from_numpy(q1).to(dev), torch.from_numpy(q2).to(dev)
+    drift = 0.01 * torch.randn(base1.shape, generator=gen, device=dev, dtype=base1.dtype)
+    if world > 1:
+        plain_handshake = fs.gather.handshake
+
+        def skewed_handshake():
+            plain_handshake()
+            if rank == world - 1:
+                torch.cuda._sleep(3_000_000)    # ~1.5 ms at 1.9 GHz, longer than a whole solve of this size
+        fs.gather.handshake = skewed_handshake
+    outs = [fs.solve(base1 + t * drift, base2) for t in range(n_steps)]
+    torch.cuda.synchronize()
+    for t, got in enumerate(outs):
+        want = eng_g.solve(pl, base1 + t * drift, base2)
+        torch.cuda.synchronize()
+        assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status), f"rank {rank} step {t}"
+        assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad), f"rank {rank} step {t}"
+    print("BACK_TO_BACK_OK", rank, n_steps, flush=True)
     fs.close()
     print("PEER_GATHER_OK", rank, flush=True)
     dist.barrier()

@@ -84,3 +84,51 @@ def test_extension_closed_forms():
     assert np.abs(a.grad[0, 0:3] - np.array([0, -2.0, 0])).max() < 1e-3
     assert np.abs(a.grad[0, 0:3] + a.grad[0, 6:9]).max() < 1e-6
     eng.close()
+
+
+# ---- pinned: goldens produced by the REFERENCE'S OWN solve_lp_pdip / finite-difference gradient, fed by its own
+# per-primitive problem_matrices through an assembly patched in exactly two places (oracle/gen_golden_extensions.py):
+# case 4 with the first primitive's blocks padded (combine_problem_matrices.py:58-67 as intended) and a hand-assembled
+# ellipsoid SOC block (Report.pdf section 3.1.5 eq. 27).  41 type pairs + offsets, 2,400 pairs.
+def _check_against_reference_goldens(res):
+    from conftest import load_golden
+    g = load_golden("extensions")
+    assert int(g["status"].sum()) == 0 and int(g["case4"].sum()) >= 360
+    assert np.array_equal(res["status"], g["status"])
+    assert np.array_equal(res["iters"], g["iters"])                                  # identical iteration counts
+    a_err = np.abs(res["alpha"] - g["alpha"]) / np.maximum(np.abs(g["alpha"]), 1.0)
+    assert a_err.max() < 1e-8, a_err.max()
+    g_err = np.abs(res["grad"] - g["grad"]).max(axis=1) / np.abs(g["grad"]).max(axis=1)
+    assert g_err.max() < 1e-6, g_err.max()                                           # the reference's FD values
+    return g
+
+
+def _solve_extension_goldens(solve):
+    from conftest import load_golden
+    g = load_golden("extensions")
+    return solve((g["shape_records"], g["A"], g["b"]), g["idx1"], g["idx2"], g["pose1"], g["pose2"])
+
+
+def test_oracle_extensions_vs_reference_solver(oracle):
+    r = _solve_extension_goldens(lambda t, i1, i2, p1, p2: oracle.solve_batch(*t, i1, i2, p1, p2, grad_mode=oracle.GRAD_FD,
+                                                                              fix_case4=True))
+    _check_against_reference_goldens(r)
+
+
+def test_twin_extensions_vs_reference_solver():
+    import twin as T
+    T.build()
+    r = _solve_extension_goldens(lambda t, i1, i2, p1, p2: T.solve_batch(*t, i1, i2, p1, p2, fix_case4=True))
+    _check_against_reference_goldens(r)
+
+
+@pytest.mark.gpu
+def test_cuda_extensions_vs_reference_solver():
+    import dcol_trajectory_optimization_b200 as d
+
+    def solve(t, i1, i2, p1, p2):
+        eng = d.ProximityEngine(t)
+        r = eng.solve_host(i1, i2, p1, p2, fix_case4=True)
+        eng.close()
+        return dict(status=r.status, iters=r.iters, alpha=r.alpha, grad=r.grad)
+    _check_against_reference_goldens(_solve_extension_goldens(solve))

@@ -300,6 +300,7 @@ def test_peer_record_gather_two_gpus(fabric):
     if "MULTICAST_UNAVAILABLE" in r.stdout:
         pytest.skip("no NVLink multicast on this box: " + r.stdout[-300:])
     assert r.stdout.count("PEER_GATHER_OK") == 2
+    assert r.stdout.count("BACK_TO_BACK_OK") == 2     # 60 back-to-back solves, one rank's consumer delayed
 
 
 def test_proximity_batch_convenience_and_pinned_buffers(dcol):
@@ -416,5 +417,53 @@ def test_fused_sharded_solver_single_rank(dcol):
     assert torch.equal(got.alpha, want.alpha) and torch.equal(got.grad, want.grad)
     assert torch.equal(got.iters, want.iters) and torch.equal(got.status, want.status)
     fs.close()
+    plan.close()
+    eng.close()
+
+
+@pytest.mark.parametrize("n_pairs", [40, 3_001, 400_003])
+def test_lane_refill_matches_one_pair_per_thread(dcol, n_pairs):
+    """The lane-refill kernels (a warp owns a chunk of pairs, finished lanes take the next pre-initialised pair from a
+    shared-memory pool) and the one-pair-per-thread kernels run the same per-pair operations: identical status words
+    and iteration counts, values equal to rounding (separately compiled kernels contract multiply-adds differently),
+    in array mode, with the 6-wide gradient (DCOL_WANT_GRAD1) and in record mode, for groups smaller than a warp,
+    ragged groups and groups of several generations per warp; with a tolerance that ends some pairs at iteration 0
+    and an iteration cap that fails others."""
+    import torch
+    from dcol_trajectory_optimization_b200 import workloads as W
+    from dcol_trajectory_optimization_b200.engine import records_to_result
+    shapes, i1, i2, p1, p2 = W.config4_batch(n_pairs, seed=77)
+    eng = dcol.ProximityEngine(shapes)
+    plan = eng.plan(i1, i2)
+    d1, d2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+
+    def close(x, y, tol):
+        assert torch.equal(x.isnan(), y.isnan())
+        ok = ~x.isnan()
+        return bool(((x[ok] - y[ok]).abs() <= tol * torch.maximum(y[ok].abs(), torch.ones_like(y[ok]))).all())
+
+    for tol, max_iter in ((1e-6, 50), (1e-6, 7), (5.0, 50)):
+        a = eng.solve(plan, d1, d2, tol=tol, max_iter=max_iter, lane_refill=True)
+        b = eng.solve(plan, d1, d2, tol=tol, max_iter=max_iter, one_pair_per_thread=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.status, b.status) and torch.equal(a.iters, b.iters)
+        assert close(a.alpha, b.alpha, 1e-11) and close(a.contact, b.contact, 1e-9) and close(a.grad, b.grad, 1e-8)
+        if max_iter == 7:
+            assert int((a.status == 1).sum()) > 0          # some pairs hit the cap
+        if tol == 5.0:
+            assert int((a.iters == 0).sum()) > 0           # some pairs converge at the initial point
+        g1 = eng.solve(plan, d1, d2, tol=tol, max_iter=max_iter, grad1=True, want_contact=False, lane_refill=True)
+        torch.cuda.synchronize()
+        assert g1.grad.shape == (n_pairs, 6)
+        assert torch.equal(g1.grad.view(torch.int64), a.grad[:, :6].contiguous().view(torch.int64))      # same kernel: bits
+        assert torch.equal(g1.alpha.view(torch.int64), a.alpha.view(torch.int64)) and torch.equal(g1.iters, a.iters)
+        rec = torch.full((n_pairs + 2, 14), -7.0, dtype=torch.float64, device="cuda")
+        eng.solve_records(plan, d1, d2, [rec[1:].data_ptr()], tol=tol, max_iter=max_iter, lane_refill=True)
+        torch.cuda.synchronize()
+        assert float(rec[0, 0]) == -7.0 and float(rec[-1, -1]) == -7.0       # canaries either side of the window
+        r = records_to_result(rec[1:-1], plan.perm())
+        assert torch.equal(r.status, a.status) and torch.equal(r.iters, a.iters)
+        assert torch.equal(r.alpha.view(torch.int64), a.alpha.view(torch.int64))
+        assert torch.equal(r.grad.contiguous().view(torch.int64), a.grad.view(torch.int64))
     plan.close()
     eng.close()
