@@ -406,6 +406,59 @@ def main():
                "api": "dcol_proximity_batch_host (ProximityEngine.solve_host), page-locked NumPy buffers, "
                       "includes the per-chunk plan (counting sort)"}
 
+    # ---- end to end on the scene workload (config 5) through the scene entry point: only poses cross PCIe on the way in ----
+    e2e_scene = None
+    if not args.no_e2e and world == 1:
+        from dcol_trajectory_optimization_b200 import workloads as Wl
+        from dcol_trajectory_optimization_b200.shapes import flatten_shapes as _flat
+        n_obs, n_knots = 1024, 100
+        n_cand = max(1, min(B, 1 << 23) // (n_obs * n_knots))
+        rng5 = np.random.default_rng(2)
+        shapes5 = [Wl.SphereMRP(0.25)] + Wl.quadrotor_obstacle_shapes()
+        obs_pose = np.concatenate([rng5.uniform([-8.0, -2.5, 1.0], [8.0, 2.5, 6.0], size=(n_obs, 3)),
+                                   rng5.normal(size=(n_obs, 3)) * 0.5], axis=1)
+        obs_shape = (1 + (np.arange(n_obs) % 11)).astype(np.int32)
+        knots = np.linspace([-8.0, 0.0, 4.0], [8.0, 0.0, 4.0], n_knots)
+        Ms = n_cand * n_knots
+        hv = d.pinned_empty((Ms, 6))
+        hv[:] = 0.0
+        hv[:, :3] = (knots[None] + rng5.normal(size=(n_cand, n_knots, 3)) * 0.3).reshape(Ms, 3)
+        eng5 = d.ProximityEngine(_flat(shapes5), device=local_rank)
+        sout = d.SceneResult(alpha=d.pinned_empty((Ms, n_obs)), grad1=d.pinned_empty((Ms, n_obs, 6)),
+                             iters=d.pinned_empty((Ms, n_obs), np.int32), status=d.pinned_empty((Ms, n_obs), np.int32))
+        for _ in range(2):
+            eng5.solve_scene_host(0, hv, obs_shape, obs_pose, out=sout)
+        t = time.perf_counter()
+        n_rep = max(3, args.steps // 2)
+        for _ in range(n_rep):
+            eng5.solve_scene_host(0, hv, obs_shape, obs_pose, out=sout)
+        dt5 = (time.perf_counter() - t) / n_rep
+        # the same pairs with inputs resident on the device (plan reused), for the e2e / device ratio
+        i1s, i2s = np.zeros(Ms * n_obs, np.int32), np.tile(obs_shape, Ms)
+        plan5 = eng5.plan(i1s, i2s)
+        q1 = torch.from_numpy(np.repeat(np.asarray(hv), n_obs, axis=0)).to(dev)
+        q2 = torch.from_numpy(np.tile(obs_pose, (Ms, 1))).to(dev)
+        o5 = None
+        ev5 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for s_ in range(2 + n_rep):
+            if s_ == 2:
+                ev5[0].record()
+            o5 = eng5.solve(plan5, q1, q2, want_contact=False, grad1=True, out=o5)
+        ev5[1].record()
+        torch.cuda.synchronize()
+        dev5 = Ms * n_obs / (ev5[0].elapsed_time(ev5[1]) * 1e-3 / n_rep)
+        assert np.array_equal(sout.iters.ravel(), o5.iters.cpu().numpy())
+        e2e_scene = {"value": Ms * n_obs / dt5, "unit": UNIT, "pairs_per_step": Ms * n_obs, "ms_per_step": dt5 * 1e3,
+                     "h2d_bytes_per_step": int(Ms * 48 + n_obs * 52), "d2h_bytes_per_step": int(Ms * n_obs * (8 + 48 + 4 + 4)),
+                     "device_resident_value": dev5, "e2e_over_device": (Ms * n_obs / dt5) / dev5,
+                     "failed_pairs": int((sout.status != 0).sum()),
+                     "workload": f"config5: sphere victim, {n_cand} candidates x {n_knots} knots x {n_obs} obstacles",
+                     "api": "dcol_proximity_scene_host (ProximityEngine.solve_scene_host): victim poses [M][6] + obstacle poses "
+                            "[n_obs][6] in, alpha + d alpha/d(victim pose) [6] + iters + status out (64 B/pair), page-locked buffers"}
+        plan5.close()
+        eng5.close()
+        del q1, q2, o5
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -430,6 +483,7 @@ def main():
             "clocks": clocks,
             **(gather_check or {}),
             "e2e": e2e,
+            "e2e_scene": e2e_scene,
             "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,

@@ -23,7 +23,8 @@ MAX_DEST, RECORD_WORDS = 8, 14
 SYMBOLS = (
     "dcol_version", "dcol_last_error", "dcol_device_count", "dcol_shape_table_create", "dcol_shape_table_destroy",
     "dcol_plan_create", "dcol_plan_destroy", "dcol_plan_size", "dcol_plan_n_groups", "dcol_plan_n_launches", "dcol_plan_refine",
-    "dcol_proximity_batch_device", "dcol_proximity_batch_jacobian", "dcol_proximity_batch_host", "dcol_host_alloc",
+    "dcol_proximity_batch_device", "dcol_proximity_batch_jacobian", "dcol_proximity_batch_host",
+    "dcol_proximity_scene_host", "dcol_host_alloc",
     "dcol_host_free",
     "dcol_proximity_batch_records", "dcol_plan_perm", "dcol_device_alloc", "dcol_device_free", "dcol_ipc_export",
     "dcol_ipc_import", "dcol_ipc_close",
@@ -85,6 +86,9 @@ def lib():
     L.dcol_proximity_batch_host.restype = C.c_int
     L.dcol_proximity_batch_host.argtypes = [vp, ip, ip, dp, dp, C.c_int64, C.c_double, C.c_int32, C.c_uint32,
                                             dp, dp, dp, ip, ip]
+    L.dcol_proximity_scene_host.restype = C.c_int
+    L.dcol_proximity_scene_host.argtypes = [vp, C.c_int32, dp, C.c_int64, ip, dp, C.c_int32, C.c_double, C.c_int32, C.c_uint32,
+                                            dp, dp, ip, ip]
     L.dcol_proximity_batch_records.restype = C.c_int
     L.dcol_proximity_batch_records.argtypes = [vp, dp, dp, C.c_double, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p),
                                                C.c_int64, dp, vp]

@@ -57,6 +57,16 @@ struct DeviceGuard {
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
+/* inside the chunk loops of the host entry points: record the error and leave the loop, so that the common epilogue
+ * still synchronises every stream (copies into the caller's buffers must not outlive the call) */
+#define DCOL_CUDA_BREAK(call)                                  \
+    {                                                          \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) {                               \
+            rc = fail_cuda(e_, #call);                         \
+            break;                                             \
+        }                                                      \
+    }
 #define DCOL_DEVICE(device)                                                   \
     DeviceGuard guard_(device);                                               \
     if (guard_.err != cudaSuccess) return fail_cuda(guard_.err, "cudaSetDevice")
@@ -105,6 +115,12 @@ struct dcol_shape_table {
     cudaStream_t streams[4] = { nullptr, nullptr, nullptr, nullptr }; /* h2d, plan, solve, d2h */
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_plan[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr },
                 ev_out[2] = { nullptr, nullptr };
+    /* scene entry point: victim poses of a chunk (two slots), the obstacles of the call */
+    double* scene_vic[2] = { nullptr, nullptr };
+    int64_t scene_vic_cap = 0;
+    double* scene_obs_pose = nullptr;
+    int32_t* scene_obs_shape = nullptr;
+    int64_t scene_obs_cap = 0;
 };
 
 struct dcol_plan {
@@ -346,6 +362,25 @@ __global__ void fill_unsupported(BatchArgs b)
     }
 }
 
+/* scene entry point: pair (m, j) = victim pose m against obstacle j, pairs ordered [m][j]; one thread per pose component */
+__global__ void scene_expand(int32_t victim_shape, const int32_t* __restrict__ obs_shape, const double* __restrict__ vic_pose,
+                             const double* __restrict__ obs_pose, int64_t n_pairs, int32_t n_obs, int32_t* __restrict__ idx1,
+                             int32_t* __restrict__ idx2, double* __restrict__ pose1, double* __restrict__ pose2)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 6 * n_pairs) return;
+    const int64_t pair = t / 6;
+    const int c = (int)(t - 6 * pair);
+    const int64_t m = pair / n_obs;
+    const int32_t j = (int32_t)(pair - m * n_obs);
+    pose1[t] = vic_pose[6 * m + c];
+    pose2[t] = obs_pose[6 * (int64_t)j + c];
+    if (c == 0 && idx1) {
+        idx1[pair] = victim_shape;
+        idx2[pair] = obs_shape[j];
+    }
+}
+
 /* FP64 FMA peak: 8 independent chains per thread, no memory traffic */
 __global__ void fp64_peak_kernel(double* out, int iters, double seed)
 {
@@ -474,6 +509,10 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
         if (T->ev_done[i]) cudaEventDestroy(T->ev_done[i]);
         if (T->ev_out[i]) cudaEventDestroy(T->ev_out[i]);
     }
+    cudaFree(T->scene_vic[0]);
+    cudaFree(T->scene_vic[1]);
+    cudaFree(T->scene_obs_pose);
+    cudaFree(T->scene_obs_shape);
     for (int i = 0; i < 4; ++i)
         if (T->streams[i]) cudaStreamDestroy(T->streams[i]);
     for (int i = 0; i < dcol_shape_table::kSide; ++i) {
@@ -735,6 +774,46 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
     return rc;
 }
 
+/* streams, events and the two sets of device scratch (chunk pairs each) of the host entry points */
+static int host_pipeline_setup(dcol_shape_table* T, int64_t chunk)
+{
+    for (int i = 0; i < 4; ++i)
+        if (!T->streams[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!T->ev_in[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_in[i], cudaEventDisableTiming));
+        if (!T->ev_plan[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_plan[i], cudaEventDisableTiming));
+        if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
+        if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i) {
+        HostScratch& S = T->scratch[i];
+        if (S.cap >= chunk) continue;
+        S.release();
+        dcol_plan_destroy(T->plans[i]);
+        T->plans[i] = nullptr;
+        cudaError_t e = cudaMalloc(&S.idx1, sizeof(int32_t) * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.idx2, sizeof(int32_t) * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.iters, sizeof(int32_t) * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.status, sizeof(int32_t) * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.pose1, sizeof(double) * 6 * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.pose2, sizeof(double) * 6 * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.alpha, sizeof(double) * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.contact, sizeof(double) * 3 * chunk);
+        if (e == cudaSuccess) e = cudaMalloc(&S.grad, sizeof(double) * 12 * chunk);
+        if (e != cudaSuccess) { /* no half-allocated slot is left behind */
+            S.release();
+            return fail_cuda(e, "host scratch allocation");
+        }
+        S.cap = chunk;
+        int rc0 = plan_alloc(T, chunk, &T->plans[i]);
+        if (rc0) {
+            S.release();
+            return rc0;
+        }
+    }
+    return 0;
+}
+
 /* Host buffers: the batch is cut into chunks that flow through three streams (copy in, plan + solve,
  * copy out) with two sets of device scratch, so PCIe traffic in both directions overlaps the solve. */
 int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, const int32_t* idx2, const double* pose1,
@@ -752,37 +831,11 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         return fail(DCOL_E_ARG, "dcol_proximity_batch_host: null buffer");
     std::lock_guard<std::mutex> lock(T->mu);
     DCOL_DEVICE(T->device);
-    for (int i = 0; i < 4; ++i)
-        if (!T->streams[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->streams[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        if (!T->ev_in[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_in[i], cudaEventDisableTiming));
-        if (!T->ev_plan[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_plan[i], cudaEventDisableTiming));
-        if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
-        if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
-    }
     const int64_t gw = (flags & DCOL_WANT_GRAD1) ? 6 : 12; /* doubles of gradient per pair */
     int64_t kChunk = 1 << 20; /* measured on B200 + PCIe 5 (chunks of 2^18..2^22): 2^20 pairs gives the best overlap */
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
-    for (int i = 0; i < 2; ++i) {
-        HostScratch& S = T->scratch[i];
-        if (S.cap >= chunk) continue;
-        S.release();
-        dcol_plan_destroy(T->plans[i]);
-        T->plans[i] = nullptr;
-        DCOL_CUDA(cudaMalloc(&S.idx1, sizeof(int32_t) * chunk));
-        DCOL_CUDA(cudaMalloc(&S.idx2, sizeof(int32_t) * chunk));
-        DCOL_CUDA(cudaMalloc(&S.iters, sizeof(int32_t) * chunk));
-        DCOL_CUDA(cudaMalloc(&S.status, sizeof(int32_t) * chunk));
-        DCOL_CUDA(cudaMalloc(&S.pose1, sizeof(double) * 6 * chunk));
-        DCOL_CUDA(cudaMalloc(&S.pose2, sizeof(double) * 6 * chunk));
-        DCOL_CUDA(cudaMalloc(&S.alpha, sizeof(double) * chunk));
-        DCOL_CUDA(cudaMalloc(&S.contact, sizeof(double) * 3 * chunk));
-        DCOL_CUDA(cudaMalloc(&S.grad, sizeof(double) * 12 * chunk));
-        S.cap = chunk;
-        int rc0 = plan_alloc(T, chunk, &T->plans[i]);
-        if (rc0) return rc0;
-    }
+    if (int rc0 = host_pipeline_setup(T, chunk)) return rc0;
     /* Four streams: copy-in, plan (counting sort), solve, copy-out.  The only host wait per chunk is for
      * that chunk's own histogram, so chunk i+1 is copied in and planned while chunk i is being solved and
      * chunk i-1 is being copied out. */
@@ -795,41 +848,137 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         dcol_plan* P = T->plans[slot];
         const int64_t k0 = ci * chunk, n = std::min(chunk, B - k0);
         if (ci >= 2) {
-            DCOL_CUDA(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));  /* inputs + perm consumed by the solve   */
-            DCOL_CUDA(cudaStreamWaitEvent(s_plan, T->ev_done[slot], 0));
-            DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));  /* previous outputs have left the device */
+            DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));  /* inputs + perm consumed by the solve   */
+            DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_plan, T->ev_done[slot], 0));
+            DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));  /* previous outputs have left the device */
         }
-        DCOL_CUDA(cudaMemcpyAsync(S.idx1, idx1 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
-        DCOL_CUDA(cudaMemcpyAsync(S.idx2, idx2 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
-        DCOL_CUDA(cudaEventRecord(T->ev_in[slot], s_in));
-        DCOL_CUDA(cudaMemcpyAsync(S.pose1, pose1 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
-        DCOL_CUDA(cudaMemcpyAsync(S.pose2, pose2 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
-        DCOL_CUDA(cudaStreamWaitEvent(s_plan, T->ev_in[slot], 0));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(S.idx1, idx1 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(S.idx2, idx2 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_in[slot], s_in));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(S.pose1, pose1 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(S.pose2, pose2 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_plan, T->ev_in[slot], 0));
         rc = plan_build(P, S.idx1, S.idx2, n, s_plan);
         if (rc) break;
-        DCOL_CUDA(cudaEventRecord(T->ev_plan[slot], s_plan));
-        DCOL_CUDA(cudaEventRecord(T->ev_in[slot], s_in)); /* now also covers the poses */
-        DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_plan[slot], 0));
-        DCOL_CUDA(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_plan[slot], s_plan));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_in[slot], s_in)); /* now also covers the poses */
+        DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_plan[slot], 0));
+        DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
         rc = dcol_proximity_batch_device(P, S.pose1, S.pose2, tol, max_iter, flags, S.alpha, S.contact, S.grad, S.iters,
                                          S.status, s_run);
         if (rc) break;
-        DCOL_CUDA(cudaEventRecord(T->ev_done[slot], s_run));
-        DCOL_CUDA(cudaStreamWaitEvent(s_out, T->ev_done[slot], 0));
-        DCOL_CUDA(cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out));
-        DCOL_CUDA(cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
-        DCOL_CUDA(cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_done[slot], s_run));
+        DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_out, T->ev_done[slot], 0));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
         if (flags & DCOL_WANT_CONTACT)
-            DCOL_CUDA(cudaMemcpyAsync(contact + 3 * k0, S.contact, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s_out));
+            DCOL_CUDA_BREAK(cudaMemcpyAsync(contact + 3 * k0, S.contact, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s_out));
         if (flags & DCOL_WANT_GRAD)
-            DCOL_CUDA(cudaMemcpyAsync(grad + gw * k0, S.grad, sizeof(double) * gw * n, cudaMemcpyDeviceToHost, s_out));
-        DCOL_CUDA(cudaEventRecord(T->ev_out[slot], s_out));
+            DCOL_CUDA_BREAK(cudaMemcpyAsync(grad + gw * k0, S.grad, sizeof(double) * gw * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_out[slot], s_out));
     }
     cudaError_t e = cudaStreamSynchronize(s_out);
     cudaStreamSynchronize(s_in);
     cudaStreamSynchronize(s_plan);
     cudaStreamSynchronize(s_run);
     if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_batch_host");
+    return rc;
+}
+
+/* Scene form of the host entry point (include/dcol.h): M victim poses x n_obs posed obstacles.  Only the M + n_obs
+ * poses cross PCIe on the way in; the kernel scene_expand broadcasts them into the pair arrays on the device.  Same
+ * chunked pipeline as dcol_proximity_batch_host; the plan of a full chunk is built once and reused (the shape pair of
+ * pair (m, j) depends on j only). */
+int dcol_proximity_scene_host(const dcol_shape_table* T_, int32_t victim_shape, const double* victim_pose, int64_t M,
+                              const int32_t* obstacle_shape, const double* obstacle_pose, int32_t n_obs, double tol,
+                              int32_t max_iter, uint32_t flags, double* alpha, double* grad1, int32_t* iters, int32_t* status)
+{
+    dcol_shape_table* T = const_cast<dcol_shape_table*>(T_);
+    if (!T || M < 0 || n_obs < 0) return fail(DCOL_E_ARG, "dcol_proximity_scene_host: bad argument");
+    if (max_iter < 1 || max_iter > DCOL_MAX_ITER) return fail(DCOL_E_ARG, "max_iter must be in 1..50");
+    if (flags & ~(uint32_t)(DCOL_FIX_CASE4 | DCOL_ONE_PAIR_PER_THREAD | DCOL_LANE_REFILL)) return fail(DCOL_E_ARG, "unknown flag");
+    if (M == 0 || n_obs == 0) return 0;
+    if (!victim_pose || !obstacle_shape || !obstacle_pose || !alpha || !status)
+        return fail(DCOL_E_ARG, "dcol_proximity_scene_host: null buffer");
+    const int32_t ns = (int32_t)T->shapes.size();
+    if (victim_shape < 0 || victim_shape >= ns) return fail(DCOL_E_INDEX, "shape index out of range");
+    for (int32_t j = 0; j < n_obs; ++j)
+        if (obstacle_shape[j] < 0 || obstacle_shape[j] >= ns) return fail(DCOL_E_INDEX, "shape index out of range");
+    std::lock_guard<std::mutex> lock(T->mu);
+    DCOL_DEVICE(T->device);
+    int64_t kChunk = 1 << 20;
+    if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
+    const int64_t Mc = std::max<int64_t>(1, std::min<int64_t>(M, kChunk / n_obs)); /* victim poses per chunk */
+    if (Mc * n_obs > 0x7fffffffLL) return fail(DCOL_E_ARG, "dcol_proximity_scene_host: too many obstacles");
+    if (int rc0 = host_pipeline_setup(T, Mc * n_obs)) return rc0;
+    if (T->scene_vic_cap < Mc) {
+        cudaFree(T->scene_vic[0]);
+        cudaFree(T->scene_vic[1]);
+        T->scene_vic[0] = T->scene_vic[1] = nullptr;
+        T->scene_vic_cap = 0;
+        DCOL_CUDA(cudaMalloc(&T->scene_vic[0], sizeof(double) * 6 * Mc));
+        DCOL_CUDA(cudaMalloc(&T->scene_vic[1], sizeof(double) * 6 * Mc));
+        T->scene_vic_cap = Mc;
+    }
+    if (T->scene_obs_cap < n_obs) {
+        cudaFree(T->scene_obs_pose);
+        cudaFree(T->scene_obs_shape);
+        T->scene_obs_pose = nullptr;
+        T->scene_obs_shape = nullptr;
+        T->scene_obs_cap = 0;
+        DCOL_CUDA(cudaMalloc(&T->scene_obs_pose, sizeof(double) * 6 * n_obs));
+        DCOL_CUDA(cudaMalloc(&T->scene_obs_shape, sizeof(int32_t) * n_obs));
+        T->scene_obs_cap = n_obs;
+    }
+    cudaStream_t s_in = T->streams[0], s_run = T->streams[2], s_out = T->streams[3];
+    const uint32_t solve_flags = flags | (grad1 ? (uint32_t)(DCOL_WANT_GRAD | DCOL_WANT_GRAD1) : 0u);
+    int rc = 0;
+    int64_t planned[2] = { -1, -1 }; /* pair count plans[0] (full chunks) / plans[1] (the last, shorter chunk) were built for */
+    const int64_t n_chunks = (M + Mc - 1) / Mc;
+    for (int64_t ci = 0; ci < n_chunks && rc == 0; ++ci) {
+        const int slot = (int)(ci & 1);
+        HostScratch& S = T->scratch[slot];
+        const int64_t m0 = ci * Mc, mc = std::min(Mc, M - m0), n = mc * n_obs;
+        if (ci == 0) {
+            DCOL_CUDA_BREAK(cudaMemcpyAsync(T->scene_obs_pose, obstacle_pose, sizeof(double) * 6 * n_obs, cudaMemcpyHostToDevice, s_in));
+            DCOL_CUDA_BREAK(cudaMemcpyAsync(T->scene_obs_shape, obstacle_shape, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, s_in));
+        }
+        if (ci >= 2) {
+            DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));  /* this slot's victim poses were consumed   */
+            DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));  /* this slot's outputs have left the device */
+        }
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(T->scene_vic[slot], victim_pose + 6 * m0, sizeof(double) * 6 * mc, cudaMemcpyHostToDevice, s_in));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_in[slot], s_in));
+        DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
+        const int which = (mc == Mc) ? 0 : 1;
+        const bool need_plan = planned[which] != n;
+        scene_expand<<<(unsigned)((6 * n + 255) / 256), 256, 0, s_run>>>(victim_shape, T->scene_obs_shape, T->scene_vic[slot],
+                                                                        T->scene_obs_pose, n, n_obs, need_plan ? S.idx1 : nullptr,
+                                                                        S.idx2, S.pose1, S.pose2);
+        DCOL_CUDA_BREAK(cudaGetLastError());
+        dcol_plan* P = T->plans[which];
+        if (need_plan) {
+            rc = plan_build(P, S.idx1, S.idx2, n, s_run);
+            if (rc) break;
+            planned[which] = n;
+        }
+        rc = dcol_proximity_batch_device(P, S.pose1, S.pose2, tol, max_iter, solve_flags, S.alpha, nullptr, grad1 ? S.grad : nullptr,
+                                         S.iters, S.status, s_run);
+        if (rc) break;
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_done[slot], s_run));
+        DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_out, T->ev_done[slot], 0));
+        const int64_t k0 = m0 * n_obs;
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA_BREAK(cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
+        if (iters) DCOL_CUDA_BREAK(cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
+        if (grad1) DCOL_CUDA_BREAK(cudaMemcpyAsync(grad1 + 6 * k0, S.grad, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, s_out));
+        DCOL_CUDA_BREAK(cudaEventRecord(T->ev_out[slot], s_out));
+    }
+    cudaError_t e = cudaStreamSynchronize(s_out);
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_run);
+    if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_scene_host");
     return rc;
 }
 

@@ -638,6 +638,11 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
             const int64_t warps = (g.args.count + a.b.per_warp - 1) / a.b.per_warp;
             const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
             const size_t smem = sizeof(double) * (kThreads / 32) * 32 * Lay::NW;
+            /* kMinBlocks CTAs of up to 42 KB each must be resident per SM: ask for the largest shared-memory
+             * carve-out (the driver's default sizes it for ONE block and would cap residency at 1-2 CTAs per SM) */
+            static const cudaError_t carve = cudaFuncSetAttribute(pair_kernel_refill<P1, P2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                                  (int)cudaSharedmemCarveoutMaxShared);
+            if (carve != cudaSuccess) return carve;
             pair_kernel_refill<P1, P2><<<(unsigned)blocks, kThreads, smem, stream>>>(a);
             return cudaGetLastError();
         }

@@ -69,6 +69,15 @@ class BatchResult:
                 "iters_hist": {int(i): int(c) for i, c in enumerate(hist) if c}}
 
 
+@dataclass
+class SceneResult:
+    """Outputs of ``ProximityEngine.solve_scene_host`` (NumPy arrays)."""
+    alpha: object      # [M, n_obs]
+    grad1: object      # [M, n_obs, 6] d alpha / d [r1 p1] (victim pose), or None
+    iters: object      # [M, n_obs] or None
+    status: object     # [M, n_obs]
+
+
 class _DevArray:
     """A raw device address exposed through ``__cuda_array_interface__`` so torch can view it."""
 
@@ -283,6 +292,34 @@ class ProximityEngine:
             self._table, idx1.ctypes.data, idx2.ctypes.data, pose1.ctypes.data, pose2.ctypes.data, B, float(tol),
             int(max_iter), flags, out.alpha.ctypes.data, out.contact.ctypes.data if out.contact is not None else None,
             out.grad.ctypes.data if out.grad is not None else None, out.iters.ctypes.data, out.status.ctypes.data))
+        return out
+
+    def solve_scene_host(self, victim_shape: int, victim_poses, obstacle_shapes, obstacle_poses, tol: float = 1e-6,
+                         max_iter: int = 50, want_grad: bool = True, want_iters: bool = True, out: "SceneResult | None" = None,
+                         fix_case4: bool = False, one_pair_per_thread: bool = False, lane_refill: bool = False) -> "SceneResult":
+        """Every (victim pose, obstacle) pair of a scene in one call (``dcol_proximity_scene_host``): ``victim_poses``
+        ``[M, 6]`` of shape ``victim_shape`` against ``obstacle_shapes[j]`` at ``obstacle_poses[j]`` (``[n_obs, 6]``).  NumPy
+        in, NumPy out: ``alpha[M, n_obs]``, ``grad1[M, n_obs, 6]`` = d alpha / d(victim r, p) — the part of the gradient the
+        reference's systems keep (``cluttered_hallway_quadrotor.py:161-163``) — ``iters``, ``status``.  Only the poses
+        cross PCIe on the way in; they are broadcast into pairs on the device."""
+        vp = np.ascontiguousarray(victim_poses, dtype=np.float64).reshape(-1, 6)
+        osh = np.ascontiguousarray(obstacle_shapes, dtype=np.int32).reshape(-1)
+        op = np.ascontiguousarray(obstacle_poses, dtype=np.float64).reshape(-1, 6)
+        M, n_obs = int(vp.shape[0]), int(osh.shape[0])
+        if op.shape[0] != n_obs:
+            raise ValueError("obstacle_shapes and obstacle_poses must describe the same number of obstacles")
+        if out is None:
+            out = SceneResult(alpha=np.empty((M, n_obs)), grad1=np.empty((M, n_obs, 6)) if want_grad else None,
+                              iters=np.empty((M, n_obs), np.int32) if want_iters else None,
+                              status=np.empty((M, n_obs), np.int32))
+        if out.alpha.shape != (M, n_obs) or out.status.shape != (M, n_obs):
+            raise ValueError(f"out.alpha / out.status must have shape ({M}, {n_obs})")
+        flags = ((FIX_CASE4 if fix_case4 else 0) | (ONE_PAIR_PER_THREAD if one_pair_per_thread else 0)
+                 | (LANE_REFILL if lane_refill else 0))
+        _lib.check(_lib.lib().dcol_proximity_scene_host(
+            self._table, int(victim_shape), vp.ctypes.data, M, osh.ctypes.data, op.ctypes.data, n_obs, float(tol),
+            int(max_iter), flags, out.alpha.ctypes.data, out.grad1.ctypes.data if out.grad1 is not None else None,
+            out.iters.ctypes.data if out.iters is not None else None, out.status.ctypes.data))
         return out
 
     # ------------------------------------------------------------------ debugging

@@ -166,6 +166,22 @@ int dcol_proximity_batch_jacobian(const dcol_plan* plan, const double* d_pose1, 
                                   int32_t max_iter, uint32_t flags, double* d_alpha, double* d_contact,
                                   double* d_grad, double* d_jac, int32_t* d_iters, int32_t* d_status, void* stream);
 
+/* (new) SCENE form of the host entry point: M poses of ONE victim shape against n_obs posed obstacles, i.e. every
+ * (victim pose, obstacle) pair — what the reference's systems evaluate knot by knot and obstacle by obstacle
+ * (systems/cluttered_hallway_quadrotor.py:127-133 for 1 - alpha, :155-163 for the gradient, of which only d alpha /
+ * d(victim pose) = g[0:6] is kept), for all knots of all rollout / line-search candidates in one call.
+ * HOST pointers.  Only M*6 + n_obs*6 doubles go to the device (the poses are broadcast into pairs there) and
+ * 8 + 4 [+ 4] [+ 48] bytes per pair come back, instead of 104 in / 112 out per pair through dcol_proximity_batch_host.
+ *   victim_pose   : [M][6] rows (r, p)          obstacle_shape : [n_obs] indices into the table
+ *   obstacle_pose : [n_obs][6]
+ *   alpha, status : [M][n_obs]                  iters : [M][n_obs] or NULL
+ *   grad1         : [M][n_obs][6] = d alpha / d [r1 p1], or NULL (then no gradient is computed)
+ * flags: DCOL_FIX_CASE4 | DCOL_ONE_PAIR_PER_THREAD | DCOL_LANE_REFILL.  Calls on one table are serialised. */
+int dcol_proximity_scene_host(const dcol_shape_table* table, int32_t victim_shape, const double* victim_pose, int64_t M,
+                              const int32_t* obstacle_shape, const double* obstacle_pose, int32_t n_obs, double tol,
+                              int32_t max_iter, uint32_t flags, double* alpha, double* grad1, int32_t* iters,
+                              int32_t* status);
+
 /* Record mode, for multi-GPU use: every pair's results go out as ONE 112-byte record
  *     { double alpha; double grad[12]; int32 iters; int32 status; }
  * written in PLAN order (record i belongs to pair dcol_plan_perm()[i]) at dest[d] + 14 * (record_offset + i)

@@ -340,7 +340,7 @@ def test_abi_argument_errors_and_concurrent_callers(dcol):
     assert b"null buffer" in L.dcol_last_error()
     assert L.dcol_proximity_batch_device(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 51, 3, out.alpha.data_ptr(),
                                          out.contact.data_ptr(), out.grad.data_ptr(), out.iters.data_ptr(), out.status.data_ptr(), None) == -1
-    assert L.dcol_proximity_batch_device(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 50, 64, out.alpha.data_ptr(),
+    assert L.dcol_proximity_batch_device(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 50, 1 << 12, out.alpha.data_ptr(),
                                          out.contact.data_ptr(), out.grad.data_ptr(), out.iters.data_ptr(), out.status.data_ptr(), None) == -1
     arr = (C.c_void_p * 1)(out.grad.data_ptr() + 8)
     assert L.dcol_proximity_batch_records(plan._handle, d1.data_ptr(), d2.data_ptr(), 1e-6, 50, 0, 1, arr, 0, None, None) == -1

@@ -241,3 +241,51 @@ def test_gpu_jacobian_unsupported_and_failed_pairs_are_nan():
     torch.cuda.synchronize()
     assert (res.status.cpu().numpy()[1:] == 1).all() and np.isnan(res.jac.cpu().numpy()[1:]).all()
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_jacobian_vs_dense_kkt_differentiation_and_finite_differences():
+    """The CUDA Jacobian against checks that share no code with the kernel (nor with its host twin):
+    (1) the dense NumPy KKT differentiation above, evaluated at the iterate (x, s, z) the GPU itself returned
+        (``dcol_debug_trace_pair``) on the oracle's assembly of (G, h) — all 40 type pairs;
+    (2) central differences of contact points / alpha of tol = 1e-12 solves run on the GPU."""
+    import torch
+    import dcol_trajectory_optimization_b200 as d
+    shapes, i1, i2, p1, p2 = W.config4_batch(240, seed=5)
+    rec, A, b = flatten_shapes(shapes)
+    eng = d.ProximityEngine((rec, A, b), device=0)
+    plan = eng.plan(i1, i2)
+    res = eng.solve(plan, torch.as_tensor(p1, device="cuda"), torch.as_tensor(p2, device="cuda"), want_jac=True)
+    torch.cuda.synchronize()
+    J = res.jac.cpu().numpy()
+    assert (res.status.cpu().numpy() == 0).all() and np.isfinite(J).all()
+    errs = []
+    for k in range(len(i1)):
+        t = eng.trace_pair(i1[k], i2[k], p1[k], p2[k])
+        assert t["status"] == 0
+        Jd = dense_jacobian(rec, A, b, i1[k], i2[k], p1[k], p2[k], t["x"], t["s"], t["z"])
+        errs.append(np.abs(J[k] - Jd).max() / max(1.0, np.abs(Jd).max()))
+    errs = np.array(errs)
+    assert np.median(errs) < 1e-8 and errs.max() < 5e-6, (np.median(errs), errs.max())
+
+    # (2) finite differences of tight GPU solves
+    n, h = 120, 1e-6
+    th = np.concatenate([p1[:n], p2[:n]], axis=1)
+    Jfd = np.zeros((n, 4, 12))
+    for j in range(12):
+        tp, tm = th.copy(), th.copy()
+        tp[:, j] += h
+        tm[:, j] -= h
+        rp = eng.solve_host(i1[:n], i2[:n], tp[:, :6].copy(), tp[:, 6:].copy(), tol=1e-12, want_grad=False)
+        rm = eng.solve_host(i1[:n], i2[:n], tm[:, :6].copy(), tm[:, 6:].copy(), tol=1e-12, want_grad=False)
+        Jfd[:, :3, j] = (rp.contact - rm.contact) / (2 * h)
+        Jfd[:, 3, j] = (rp.alpha - rm.alpha) / (2 * h)
+    ok = np.isfinite(Jfd).reshape(n, -1).all(axis=1)
+    assert ok.sum() >= 115
+    for tol, med, p90 in ((1e-6, 5e-4, 1e-2), (1e-9, 5e-5, 2e-3)):
+        out = eng.solve(plan, torch.as_tensor(p1, device="cuda"), torch.as_tensor(p2, device="cuda"), tol=tol, want_jac=True)
+        torch.cuda.synchronize()
+        err = _rel(out.jac.cpu().numpy()[:n][ok], Jfd[ok])
+        assert np.median(err) < med and np.quantile(err, 0.9) < p90, (tol, np.median(err), np.quantile(err, 0.9))
+    plan.close()
+    eng.close()

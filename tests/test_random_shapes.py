@@ -124,3 +124,50 @@ def test_jacobian_on_random_shapes_matches_dense_kkt(twin, oracle):
         errs.append(np.abs(out["jac"][k] - Jd).max() / max(1.0, np.abs(Jd).max()))
     errs = np.array(errs)
     assert len(errs) > 150 and np.median(errs) < 1e-8 and np.quantile(errs, 0.98) < 1e-5, (np.median(errs), errs.max())
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("offsets", [False, True])
+def test_cuda_follows_oracle_on_random_shapes(oracle, offsets):
+    """The same property test through the C ABI on the GPU: runtime-face-count classes (``polyn`` 4..32 faces,
+    ``pgonn`` 3..12 sides), body-frame offsets, random sizes, all 21 x 21 ordered shape pairs, against the oracle."""
+    import dcol_trajectory_optimization_b200 as d
+    rng = np.random.default_rng(2024 + offsets)
+    shapes = _shape_zoo(rng, offsets)
+    rec, A, b = flatten_shapes(shapes)
+    i1, i2, p1, p2 = _batch(rng, shapes, 100_000)
+    ref = oracle.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=oracle.GRAD_EXACT, fix_case4=True)
+    eng = d.ProximityEngine((rec, A, b))
+    out = eng.solve_host(i1, i2, p1, p2, fix_case4=True)
+    eng.close()
+    assert np.array_equal(out.status, ref["status"])
+    ok = ref["status"] == 0
+    assert ok.mean() > 0.995
+    flips = out.iters[ok] != ref["iters"][ok]
+    assert flips.mean() < 2e-4, flips.sum()
+    same = ok & (out.iters == ref["iters"])
+    rel = np.abs(out.alpha[same] - ref["alpha"][same]) / np.maximum(np.abs(ref["alpha"][same]), 1.0)
+    assert rel.max() < 1e-8, rel.max()
+    gscale = np.maximum(np.abs(ref["grad"][same]).max(axis=1), 1e-12)
+    gerr = np.abs(out.grad[same] - ref["grad"][same]).max(axis=1) / gscale
+    assert np.median(gerr) < 1e-9 and np.quantile(gerr, 0.999) < 1e-6, (np.median(gerr), np.quantile(gerr, 0.999))
+    cscale = np.maximum(np.abs(ref["contact"][same]).max(axis=1), 1.0)
+    cerr = np.abs(out.contact[same] - ref["contact"][same]).max(axis=1) / cscale
+    assert np.quantile(cerr, 0.999) < 1e-7
+
+
+@pytest.mark.gpu
+def test_cuda_face_count_limit_is_reported():
+    """DCOL_MAX_FACES = 32 half-spaces per polytope / polygon (the reference has no limit; its largest shape, A1 of
+    systems/polytopes.jld2, has 14): a larger shape is rejected when the table is created, with DCOL_E_SHAPE."""
+    import dcol_trajectory_optimization_b200 as d
+    from dcol_trajectory_optimization_b200._lib import DcolError
+    rng = np.random.default_rng(1)
+    ok = d.ProximityEngine([_random_polytope(rng, 32), d.SphereMRP(0.5)])
+    r = ok.solve_host([0], [1], np.zeros((1, 6)), np.array([[4.0, 0, 0, 0, 0, 0]]))
+    assert r.status[0] == 0
+    ok.close()
+    with pytest.raises(DcolError) as e:
+        d.ProximityEngine([_random_polytope(rng, 33), d.SphereMRP(0.5)])
+    assert e.value.code == -2

@@ -13,11 +13,10 @@ PY
 }
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/ab2_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/ab2_pytest.log
 run plain DCOL_REFILL=0
-run refill_auto X=1
-for g in 2 4 8 16 32; do run refill_g$g DCOL_REFILL_GEN=$g; done
-run inl_auto DCOL_LIB=$PWD/dcol_trajectory_optimization_b200/libdcol_b200_inl.so
+run refill_auto DCOL_REFILL=1
+for g in 1 2 4 8 16; do run refill_g$g DCOL_REFILL=1 DCOL_REFILL_GEN=$g; done
 EXTRA_ARGS="--workload config5"
 run c5_plain DCOL_REFILL=0
-run c5_refill_auto X=1
-run c5_refill_g4 DCOL_REFILL_GEN=4
-run c5_inl DCOL_LIB=$PWD/dcol_trajectory_optimization_b200/libdcol_b200_inl.so
+run c5_refill_auto DCOL_REFILL=1
+run c5_refill_g4 DCOL_REFILL=1 DCOL_REFILL_GEN=4
+run c5_refill_g16 DCOL_REFILL=1 DCOL_REFILL_GEN=16
