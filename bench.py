@@ -165,6 +165,51 @@ def parity_vs_python_reference(check_path, device=0):
             "note": "reference gradient is a forward finite difference (h = 2^-26): its own noise is up to 5.4e-7"}
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the CURRENT kernels
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py --json from `ncu --set full` of this bench command);
+    null when no capture of the current kernels is committed."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        t = json.load(open(path))
+        return {"traffic": t["mean_dram_bytes_per_launch"],
+                "traffic_detail": {"unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                                   "pairs_per_launch": t["pairs_per_launch"],
+                                   "algorithmic_bytes_per_launch": t["pairs_per_launch"] * 212,
+                                   "launches_captured": t["launches"], "source": "profiles/r02_ncu_traffic.json <- " + t["source"]}}
+    except Exception:
+        return {"traffic": None, "traffic_detail": {"note": "no ncu capture of the current kernels committed"}}
+
+
+def parity_sample(eng_shapes, device, n=1 << 18, seed=4321):
+    """Parity of the CUDA path with the oracle on a fresh sample of the workload, reported in the line: status /
+    iteration-count mismatches, alpha and gradient errors, and how many pairs are ROUNDING-SENSITIVE in the reference's
+    own arithmetic (its gradient moves by more than 1e-6 when the oracle is merely compiled with fused multiply-adds;
+    those pairs are held to 1e-3 by the tests, every other pair to 1e-6)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import dcol_trajectory_optimization_b200 as d
+    (rec, A, b), i1, i2, p1, p2 = make_batch(n, seed)
+    ref = O.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=O.GRAD_EXACT)
+    fma = O.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=O.GRAD_EXACT, fma=True)
+    eng = d.ProximityEngine((rec, A, b), device=device)
+    res = eng.solve_host(i1, i2, p1, p2)
+    eng.close()
+    gscale = np.abs(ref["grad"]).max(axis=1)
+    sens = (np.abs(fma["grad"] - ref["grad"]).max(axis=1) / gscale) > 1e-6
+    gerr = np.abs(res.grad - ref["grad"]).max(axis=1) / gscale
+    aerr = np.abs(res.alpha - ref["alpha"]) / np.maximum(np.abs(ref["alpha"]), 1.0)
+    return {"pairs": n, "status_mismatches": int((res.status != ref["status"]).sum()),
+            "iteration_count_mismatches": int((res.iters != ref["iters"]).sum()),
+            "oracle_fma_build_iteration_count_mismatches": int((fma["iters"] != ref["iters"]).sum()),
+            "max_alpha_rel_err": float(aerr.max()), "pairs_with_grad_err_above_1e-6": int((gerr > 1e-6).sum()),
+            "rounding_sensitive_pairs": int(sens.sum()),
+            "max_grad_rel_err_excluding_rounding_sensitive": float(gerr[~sens].max()),
+            "max_grad_rel_err": float(gerr.max()),
+            "note": "oracle = C restatement of the reference pinned to reference-generated goldens; gradient vs the exact "
+                    "derivative of the reference's frozen-(x, z) Lagrangian"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
     itself is pure Python and cannot be compiled into oracle/_ref), all host threads."""
@@ -215,6 +260,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-python-reference", action="store_true", help="skip timing the unmodified Python reference (baseline/_ref)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sizes", action="store_true", help="skip the config5_full / config4_2p26 extra measurements")
+    ap.add_argument("--no-parity-sample", action="store_true", help="skip the CUDA-vs-oracle parity sample (N = 1 only)")
     ap.add_argument("--no-coherent", action="store_true", help="skip the coherent re-solve line (N = 1 only)")
     ap.add_argument("--no-jacobian", action="store_true", help="skip the solution-Jacobian throughput line (N = 1 only)")
     args = ap.parse_args()
@@ -459,6 +506,78 @@ def main():
         eng5.close()
         del q1, q2, o5
 
+    # ---- BASELINE.json configs at their stated sizes, as extra keys (not `value`) ----
+    extra_sizes = {}
+    if not args.no_sizes:
+        del_keep = (d1, d2)      # the main batch stays resident; these runs allocate their own inputs on the device
+
+        def timed(engine, plan, q1, q2, reps=3):
+            out = None
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for s_ in range(2 + reps):
+                if s_ == 2:
+                    barrier()
+                    evs[0].record()
+                out = engine.solve(plan, q1, q2, want_contact=False, out=out)
+            evs[1].record()
+            barrier()
+            t_ms = torch.tensor([evs[0].elapsed_time(evs[1]) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            fails = (out.status != 0).sum().to(torch.float64).reshape(1)
+            if world > 1:
+                dist.all_reduce(fails)
+            return float(t_ms), int(fails), float(out.iters.double().mean())
+
+        # config 5 at its full size: 1024 obstacles x 100 knots x 256 candidates = 26,214,400 pairs, candidates sharded
+        from dcol_trajectory_optimization_b200 import workloads as Wl
+        from dcol_trajectory_optimization_b200.shapes import flatten_shapes as _flat
+        n_obs, n_knots, n_cand = 1024, 100, 256
+        clo, chi = parallel.shard_bounds(n_cand, rank, world)
+        rng5 = np.random.default_rng(2)
+        obs = torch.from_numpy(np.concatenate([rng5.uniform([-8.0, -2.5, 1.0], [8.0, 2.5, 6.0], size=(n_obs, 3)),
+                                               rng5.normal(size=(n_obs, 3)) * 0.5], axis=1)).to(dev)
+        knots = np.linspace([-8.0, 0.0, 4.0], [8.0, 0.0, 4.0], n_knots)
+        vic = np.zeros((n_cand, n_knots, 6))
+        vic[..., :3] = knots[None] + rng5.normal(size=(n_cand, n_knots, 3)) * 0.3
+        vic = torch.from_numpy(vic[clo:chi].reshape(-1, 6)).to(dev)
+        Ms = vic.shape[0]
+        q1 = vic.repeat_interleave(n_obs, dim=0).contiguous()
+        q2 = obs.repeat(Ms, 1).contiguous()
+        eng5 = d.ProximityEngine(_flat([Wl.SphereMRP(0.25)] + Wl.quadrotor_obstacle_shapes()), device=local_rank)
+        plan5 = eng5.plan(torch.zeros(Ms * n_obs, dtype=torch.int32), (1 + torch.arange(n_obs, dtype=torch.int32) % 11).repeat(Ms))
+        t5, f5, it5 = timed(eng5, plan5, q1, q2)
+        extra_sizes["config5_full"] = {"pairs": n_obs * n_knots * n_cand, "n_gpus": world, "ms_per_step": t5,
+                                       "value": n_obs * n_knots * n_cand / (t5 * 1e-3), "unit": UNIT, "failed_pairs": f5,
+                                       "mean_pdip_iters": it5, "scaling": "strong (fixed 26,214,400 pairs, candidates sharded)",
+                                       "outputs": "alpha + grad[12] + iters + status, device resident, no gather"}
+        plan5.close()
+        eng5.close()
+        del q1, q2, vic, obs
+        # config 4 at 2^26 pairs per GPU (the top of BASELINE.json's 1M-64M sweep): poses drawn on the device from the same
+        # distribution (torch generator), 40 type pairs round-robin
+        n26 = 1 << 26
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(99 + rank)
+
+        def ball(radius):
+            u = torch.randn((n26, 3), generator=gen, device=dev, dtype=torch.float64)
+            u /= u.norm(dim=1, keepdim=True)
+            return u * (radius * torch.rand((n26, 1), generator=gen, device=dev, dtype=torch.float64))
+        q1 = torch.cat([ball(1.0), 0.5 * torch.randn((n26, 3), generator=gen, device=dev, dtype=torch.float64)], dim=1)
+        q2 = torch.cat([ball(6.0), 0.5 * torch.randn((n26, 3), generator=gen, device=dev, dtype=torch.float64)], dim=1)
+        pairs40 = torch.from_numpy(np.asarray(Wl.supported_type_pairs(Wl.config4_shapes()), dtype=np.int32))
+        sel = torch.arange(n26) % len(pairs40)
+        eng4 = d.ProximityEngine(_flat(Wl.config4_shapes()), device=local_rank)
+        plan26 = eng4.plan(pairs40[sel, 0].contiguous(), pairs40[sel, 1].contiguous())
+        t26, f26, it26 = timed(eng4, plan26, q1, q2, reps=2)
+        extra_sizes["config4_2p26"] = {"pairs_per_gpu": n26, "n_gpus": world, "ms_per_step": t26,
+                                       "value": n26 * world / (t26 * 1e-3), "unit": UNIT, "failed_pairs": f26,
+                                       "mean_pdip_iters": it26, "scaling": "weak"}
+        plan26.close()
+        eng4.close()
+        del q1, q2, sel
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -484,14 +603,11 @@ def main():
             **(gather_check or {}),
             "e2e": e2e,
             "e2e_scene": e2e_scene,
+            **extra_sizes,
             "gpu_launches": args.steps * n_launches,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,
-                         "traffic": 143.6e6,
-                         "traffic_detail": {"unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "pairs_per_launch": 209715,
-                                            "algorithmic_bytes_per_launch": 209715 * 212,
-                                            "source": "profiles/r01_ncu_full_14kernels.md (ncu --set full, mean of 14 specialisations "
-                                                      "at this size, captured with the contact point also written)"},
+                         **measured_traffic(),
                          "kernel": f"dcol::pair_kernel<P1,P2> ({plans[0].n_groups} specialisations, {n_launches} launches per step)",
                          "kernel_ms_per_step": kernel_ms, "model_flops_per_pair": flops / B,
                          "peak_source": "dcol_measure_fp64_peak in this run (MEASURED_PEAKS.json has no FP64 entry)",
@@ -554,6 +670,8 @@ def main():
                                         "failed_pairs_last_step": int((cout.status != 0).sum()),
                                         "note": "fixed pair list, poses drift by a random walk; plan re-ordered after every "
                                                 "solve by that solve's iteration counts (dcol_plan_refine, inside the timed region)"}
+        if world == 1 and not args.no_parity_sample:
+            line["parity_sample"] = parity_sample(None, local_rank)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             if not args.no_python_reference:

@@ -37,47 +37,34 @@ class EngineEvaluator:
     obstacle poses never change, so a solve moves only the victim poses in and (alpha, grad) out."""
 
     def __init__(self, problem: Problem, device: int = 0):
-        import torch
         from ..engine import ProximityEngine, raise_for_status
         from ..shapes import pose_of
-        self._torch, self._raise = torch, raise_for_status
+        self._raise = raise_for_status
         self.n_obs = problem.n_obs
         self.engine = ProximityEngine([problem.victim] + list(problem.obstacles), device=device)
-        self.dev = self.engine.device
-        self.obs_pose = torch.from_numpy(np.stack([pose_of(o) for o in problem.obstacles])).to(self.dev)
-        self._plans = {}
+        self.obs_shape = np.arange(1, self.n_obs + 1, dtype=np.int32)
+        self.obs_pose = np.ascontiguousarray(np.stack([pose_of(o) for o in problem.obstacles]))
         self.pair_solves = 0
         self.calls = 0
 
-    def _plan(self, M):
-        torch = self._torch
-        entry = self._plans.get(M)
-        if entry is None:
-            idx1 = torch.zeros(M * self.n_obs, dtype=torch.int32)
-            idx2 = torch.arange(1, self.n_obs + 1, dtype=torch.int32).repeat(M)
-            entry = (self.engine.plan(idx1, idx2), self.obs_pose.repeat(M, 1).contiguous())
-            self._plans[M] = entry
-        return entry
+    def evaluate(self, victim_poses: np.ndarray, want_grad: bool):
+        """``victim_poses [M, 6]`` -> ``alpha [M, n_obs]``, ``grad1 [M, n_obs, 6]`` (or None), ``status [M, n_obs]``.
+        ONE call of the scene entry point of the C ABI (``dcol_proximity_scene_host``): the victim poses go in, alpha,
+        the victim half of the gradient and the status words come out; nothing is raised."""
+        res = self.engine.solve_scene_host(0, victim_poses, self.obs_shape, self.obs_pose, want_grad=want_grad,
+                                           want_iters=False)
+        self.pair_solves += victim_poses.shape[0] * self.n_obs
+        self.calls += 1
+        return res.alpha, res.grad1, res.status
 
     def __call__(self, victim_poses: np.ndarray, want_grad: bool):
-        """``victim_poses [M, 6]`` -> ``alpha [M, n_obs]``, ``grad1 [M, n_obs, 6]`` (or None)."""
-        torch = self._torch
-        M = victim_poses.shape[0]
-        plan, pose2 = self._plan(M)
-        pose1 = torch.from_numpy(np.ascontiguousarray(victim_poses)).to(self.dev).repeat_interleave(self.n_obs, dim=0)
-        res = self.engine.solve(plan, pose1.contiguous(), pose2, want_grad=want_grad, want_contact=False)
-        status = res.status.cpu().numpy()
+        """As :meth:`evaluate`, raising what the reference raises for the first failed pair."""
+        alpha, grad, status = self.evaluate(victim_poses, want_grad)
         if status.any():
             self._raise(int(status[status != 0][0]))
-        self.pair_solves += M * self.n_obs
-        self.calls += 1
-        alpha = res.alpha.cpu().numpy().reshape(M, self.n_obs)
-        grad = res.grad[:, :6].cpu().numpy().reshape(M, self.n_obs, 6) if want_grad else None
         return alpha, grad
 
     def close(self):
-        for plan, _ in self._plans.values():
-            plan.close()
         self.engine.close()
 
 
@@ -260,31 +247,40 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
 
     tm["setup"] = clock() - t_start
 
-    def constraints(Xs, want_grad):
+    def constraints(Xs, want_grad, tolerant=False):
         nonlocal pair_solves, calls
         t0 = clock()
         try:
-            return _constraints(Xs, want_grad)
+            return _constraints(Xs, want_grad, tolerant)
         finally:
             tm["constraints"] += clock() - t0
 
-    def _constraints(Xs, want_grad):
+    def _constraints(Xs, want_grad, tolerant):
+        """tolerant: failed solves do not raise; the third return value holds, per leading index of ``Xs`` (per
+        trajectory), the status word of its first failed pair (0 = none).  Only evaluators with ``evaluate`` support it."""
         nonlocal pair_solves, calls
         lead = Xs.shape[:-1]
         poses = problem.pose_of_state(Xs).reshape(-1, 6)
-        alpha, g = evaluator(poses, want_grad)
+        failed = None
+        if tolerant and hasattr(evaluator, "evaluate"):
+            alpha, g, status = evaluator.evaluate(poses, want_grad)
+            st = status.reshape(lead[:-1] + (-1,)) if len(lead) > 1 else status.reshape(1, -1)
+            first = np.argmax(st != 0, axis=-1)
+            failed = np.take_along_axis(st, first[..., None], axis=-1)[..., 0]
+        else:
+            alpha, g = evaluator(poses, want_grad)
         pair_solves += poses.shape[0] * n_obs
         calls += 1
         hx = (1.0 - alpha).reshape(lead + (n_obs,))                     # inequality_constraints_x, e.g. piano_mover.py:66
         if not want_grad:
-            return hx, None
+            return hx, None, failed
         Jp = problem.pose_jacobian(Xs).reshape(-1, 6, nx)               # d alpha / d x = g[0:6] . d(r, p)/dx
         ghx = -np.einsum("moi,mix->mox", g, Jp).reshape(lead + (n_obs, nx))
-        return hx, ghx
+        return hx, ghx, failed
 
     for itr in range(problem.max_iters):
         passes = itr + 1
-        hx, ghx = constraints(X, True)                                   # ONE batched solve: values + gradients
+        hx, ghx, _ = constraints(X, True)                                # ONE batched solve: values + gradients
         t0 = clock()
         K, k, delta_J = core.backward_pass(X, U, hx, ghx, mu, mux, lambd, rho, reg)
         t1 = clock()
@@ -296,10 +292,21 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
             t0 = clock()
             Xn, Un = core.rollouts(X, U, K, k, ls_alphas)
             tm["rollouts"] += clock() - t0
-            hxn, _ = constraints(Xn, False)                              # ONE batched solve for all step sizes
+            hxn, _, failed = constraints(Xn, False, tolerant=True)       # ONE batched solve for all step sizes
             t0 = clock()
-            costs = core.total_cost(Xn, Un, hxn, mu, mux, lambd, rho)
+            costs = core.total_cost(Xn, Un, np.nan_to_num(hxn, nan=0.0), mu, mux, lambd, rho)
             tm["cost"] += clock() - t0
+            if failed is not None and failed.any():
+                # The sequential loop (ALTRO.py:212-234) evaluates step sizes one by one and stops at the first that
+                # lowers the cost: a PDIP failure at a LATER (smaller) step size is never seen by it and must not abort
+                # the solve; one at or before the accepted step size raises there too.
+                costs = np.where(failed != 0, np.inf, costs)
+                ok_better = np.nonzero(costs < old_cost)[0]
+                stop = int(ok_better[0]) if ok_better.size else len(ls_alphas) - 1
+                seen = np.nonzero(failed[:stop + 1])[0]
+                if seen.size:
+                    from ..engine import raise_for_status
+                    raise_for_status(int(failed[seen[0]]))
             better = np.nonzero(costs < old_cost)[0]
             if better.size:
                 c = int(better[0])
@@ -307,7 +314,7 @@ def altro_solve(problem: Problem, evaluator=None, speculative: bool = True, verb
         else:
             for a in ls_alphas:
                 Xn, Un = core.rollouts(X, U, K, k, [a])
-                hxn, _ = constraints(Xn, False)
+                hxn, _, _ = constraints(Xn, False)
                 cost = float(core.total_cost(Xn, Un, hxn, mu, mux, lambd, rho)[0])
                 if cost < old_cost:
                     alpha, accepted = a, (Xn[0].copy(), Un[0].copy(), hxn[0].copy(), cost)

@@ -124,7 +124,8 @@ struct dcol_shape_table {
 };
 
 struct dcol_plan {
-    const dcol_shape_table* table;
+    const dcol_shape_table* table; /* borrowed: the table must outlive every solve / refine of this plan ...   */
+    int device;                    /* ... but not its destruction: the plan remembers its device              */
     int64_t B, capacity;
     int32_t* d_perm;   /* [capacity] plan order -> pair index             */
     int32_t* d_counts; /* [n_shapes^2 + 1] histogram / cursor + error flag */
@@ -575,6 +576,7 @@ static int plan_alloc(const dcol_shape_table* T, int64_t capacity, dcol_plan** o
     const int32_t ns = (int32_t)T->shapes.size();
     dcol_plan* P = new dcol_plan();
     P->table = T;
+    P->device = T->device;
     P->B = 0;
     P->capacity = capacity;
     P->d_perm = nullptr;
@@ -617,7 +619,7 @@ int dcol_plan_create(const dcol_shape_table* T, const int32_t* d_idx1, const int
 void dcol_plan_destroy(dcol_plan* P)
 {
     if (!P) return;
-    DeviceGuard guard_(P->table->device);
+    DeviceGuard guard_(P->device); /* not P->table->device: the table may already have been destroyed */
     cudaFree(P->d_perm);
     cudaFree(P->d_perm_alt);
     cudaFree(P->d_gstart);
@@ -693,7 +695,7 @@ int dcol_plan_refine(dcol_plan* P, const int32_t* d_iters, void* stream_)
     if (P->B == 0 || n_groups == 0) return 0;
     if (n_groups > kRefineMaxGroups) return fail(DCOL_E_ARG, "dcol_plan_refine: at most 1024 groups");
     cudaStream_t stream = (cudaStream_t)stream_;
-    DCOL_DEVICE(P->table->device);
+    DCOL_DEVICE(P->device);
     (void)cudaGetLastError();
     const int n_bins = n_groups * kRefineBins;
     if (!P->d_perm_alt) DCOL_CUDA(cudaMalloc(&P->d_perm_alt, sizeof(int32_t) * (size_t)P->capacity));

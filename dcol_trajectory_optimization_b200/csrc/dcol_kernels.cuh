@@ -333,9 +333,12 @@ __device__ __forceinline__ int nth_set_bit(unsigned m, int r)
 /* PHASE: epilogue of the DONE slots, then initialisation of new pairs into the (then all free) slots.  Lane j works on
  * slot j.  Precondition: no FRESH slot.  Its own function so that the trip loop's live state is saved around the call
  * instead of competing with the initialisation for registers. */
+struct SlotMasks {
+    unsigned fresh, done;
+};
 template <class P1, class P2>
-__device__ DCOL_PHASE_ATTR void refill_phase(const GroupArgs<P1, P2>& a, double* pool, unsigned& fresh, unsigned& done,
-                                             int64_t& next, int64_t end)
+__device__ DCOL_PHASE_ATTR SlotMasks refill_phase(const GroupArgs<P1, P2>& a, double* pool, unsigned done, int32_t next,
+                                                  int32_t end)
 {
     typedef Solver<P1, P2> S;
     typedef RefillLayout<S> Lay;
@@ -429,12 +432,12 @@ __device__ DCOL_PHASE_ATTR void refill_phase(const GroupArgs<P1, P2>& a, double*
         done = 0;
     }
     /* initialisation: lane j takes plan position next + j into slot j */
-    const int64_t n_new = end - next < 32 ? end - next : 32;
+    const int32_t n_new = end - next < 32 ? end - next : 32;
     int st = 0;
     bool is_new = false;
     if (lane < n_new) {
         is_new = true;
-        const int64_t pos = next + lane;
+        const int64_t pos = (int64_t)next + lane;
         const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos] : a.b.first + pos;
         if (pos + 32 < end) { /* the pair this lane initialises in the NEXT phase: pull its poses into L2 now */
             const int64_t kn = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos + 32] : a.b.first + pos + 32;
@@ -458,12 +461,19 @@ __device__ DCOL_PHASE_ATTR void refill_phase(const GroupArgs<P1, P2>& a, double*
         visit_state(sv, sz, [&](int off, double& v, bool) { pool[off * 32 + lane] = v; });
         pool[Lay::META * 32 + lane] = pack_meta(pos, iters, st == S::kContinue ? 0 : st);
     }
-    fresh = __ballot_sync(0xffffffffu, is_new && st == S::kContinue);
-    done = __ballot_sync(0xffffffffu, is_new && st != S::kContinue);
-    next += n_new;
+    SlotMasks m;
+    m.fresh = __ballot_sync(0xffffffffu, is_new && st == S::kContinue);
+    m.done = __ballot_sync(0xffffffffu, is_new && st != S::kContinue);
     __syncwarp();
+    return m;
 }
 
+/* Control structure: an OUTER loop with one PHASE (a call) per turn, and inside it a call-free INNER loop of trips that
+ * runs until the pool has no FRESH slot left for a lane that needs one.  The inner loop's state (x, s, z, the relative
+ * pose; ~50-70 doubles per lane) is written to a local array when the inner loop is left and read back when it is
+ * entered again, once per generation of 32 pairs, so that nothing but a few integers is live across the call.  (With the
+ * call inside the trip loop ptxas kept ~25 doubles of loop state in the stack frame and moved them on EVERY trip; local
+ * memory then misses L1, most of which is carved out as shared memory for the pool, and the stores go to L2.) */
 template <class P1, class P2>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel_refill(const __grid_constant__ GroupArgs<P1, P2> a)
 {
@@ -473,22 +483,53 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel_refill(const
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double* pool = pool_all + w * (32 * Lay::NW);
     const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + w;
-    int64_t next = warp_id * (int64_t)a.b.per_warp;
-    if (next >= a.b.count) return;
-    const int64_t end = next + a.b.per_warp < a.b.count ? next + a.b.per_warp : a.b.count;
+    if (warp_id * (int64_t)a.b.per_warp >= a.b.count) return;
+    int32_t next = (int32_t)(warp_id * a.b.per_warp); /* a group holds fewer than 2^31 pairs (dcol_plan_create) */
+    const int32_t end = (int64_t)next + a.b.per_warp < a.b.count ? next + a.b.per_warp : (int32_t)a.b.count;
     const unsigned lt = (1u << lane) - 1u;
 
-    S sv;
-    double sz = 0.0;
+    double park[Lay::NW]; /* this lane's pair while a PHASE runs */
     bool has = false, fin = false;
     int it = 0, status = 0;
-    int32_t iters = 0;
-    int64_t pos = 0;
+    int32_t iters = 0, pos = 0;
     unsigned fresh = 0, done = 0; /* slot states, warp-uniform; a slot in neither set is free */
 
     for (;;) {
-        /* ---- settle: finished lanes park their result, lanes without a pair take a FRESH state ---- */
+        /* ---- PHASE: epilogue of the DONE slots, initialisation of up to 32 new pairs ---- */
+        {
+            const SlotMasks m = refill_phase<P1, P2>(a, pool, done, next, end);
+            fresh = m.fresh;
+            done = m.done;
+            next += end - next < 32 ? end - next : 32;
+        }
+        if (fresh == 0 && !__any_sync(0xffffffffu, has)) {
+            if (next < end) continue; /* every new pair ended inside its initialisation: next generation */
+            if (done) (void)refill_phase<P1, P2>(a, pool, done, next, end);
+            return;
+        }
+        /* ---- trips, until a lane needs a FRESH slot and there is none ---- */
+        S sv;
+        double sz = 0.0;
+        if (has) visit_state(sv, sz, [&](int off, double& v, bool) { v = park[off]; });
+        bool scaled = true; /* a parked pair was parked AFTER the scaling / tests of its current iterate */
         for (;;) {
+            /* top of an iteration for every lane that holds a pair: NT scaling of its iterate, mu, the convergence test.
+             * (The scaling is not carried around the loop: only x, s, z and the relative pose are, as in Solver::solve;
+             * a pair taken from a FRESH slot below brings the scaling of its iteration 0 with it.) */
+            if (!scaled && has && !fin) {
+                if (it >= a.b.max_iter) {
+                    fin = true;
+                    status = sv.cap_status(a.b.max_iter, iters);
+                } else {
+                    const int st = sv.scale_and_check(a.c1, a.c2, a.b.tol, it, iters, sz, nullptr);
+                    if (st != S::kContinue) {
+                        fin = true;
+                        status = st;
+                    }
+                }
+            }
+            scaled = false;
+            /* settle: finished lanes park their result, lanes without a pair take a FRESH state */
             const unsigned m_fin = __ballot_sync(0xffffffffu, has && fin);
             const unsigned m_empty = __ballot_sync(0xffffffffu, !has);
             const int n_fresh = __popc(fresh), n_fin = __popc(m_fin);
@@ -524,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel_refill(const
                 } else {
                     visit_state(sv, sz, [&](int off, double& v, bool) { v = pool[off * 32 + slot]; });
                 }
-                pos = (int64_t)(uint32_t)meta;
+                pos = (int32_t)(uint32_t)meta;
                 it = 0;
                 has = true;
                 fin = false;
@@ -543,34 +584,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel_refill(const
             done |= to_done;
             __syncwarp();
             const bool holder = __any_sync(0xffffffffu, has && fin);
-            if (fresh == 0 && (holder || next < end)) {
-                refill_phase<P1, P2>(a, pool, fresh, done, next, end);
-                continue; /* holders park, lanes without a pair load */
-            }
-            break;
-        }
-        if (!__any_sync(0xffffffffu, has)) { /* nothing in flight, nothing FRESH, nothing left to initialise */
-            if (done) refill_phase<P1, P2>(a, pool, fresh, done, next, end);
-            break;
-        }
-        /* ---- trip: one Newton step and the scaling / convergence test of the next iterate ---- */
-        if (has && !fin) {
-            int st = sv.newton_step(a.c1, a.c2, sz);
-            if (st != 0) {
-                fin = true;
-                status = st;
-                iters = it;
-            } else if (++it >= a.b.max_iter) {
-                fin = true;
-                status = sv.cap_status(a.b.max_iter, iters);
-            } else {
-                st = sv.scale_and_check(a.c1, a.c2, a.b.tol, it, iters, sz, nullptr);
-                if (st != S::kContinue) {
+            if (fresh == 0 && (holder || next < end)) break;    /* a PHASE is due */
+            if (!__any_sync(0xffffffffu, has)) break;            /* nothing in flight, nothing FRESH, nothing to initialise */
+            /* one Newton step for every lane that holds an unfinished pair */
+            if (has && !fin) {
+                const int st = sv.newton_step(a.c1, a.c2, sz);
+                if (st != 0) {
                     fin = true;
                     status = st;
+                    iters = it;
+                } else {
+                    ++it;
                 }
             }
         }
+        if (has) visit_state(sv, sz, [&](int off, double& v, bool) { park[off] = v; });
+        /* here: a PHASE is due (holders wait for a free slot, or new pairs can be initialised), or everything is finished
+         * and the DONE slots still need their epilogue — both are the next turn's PHASE; the exit test follows it */
     }
 }
 
@@ -638,10 +668,10 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
             const int64_t warps = (g.args.count + a.b.per_warp - 1) / a.b.per_warp;
             const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
             const size_t smem = sizeof(double) * (kThreads / 32) * 32 * Lay::NW;
-            /* kMinBlocks CTAs of up to 42 KB each must be resident per SM: ask for the largest shared-memory
-             * carve-out (the driver's default sizes it for ONE block and would cap residency at 1-2 CTAs per SM) */
+            /* kMinBlocks CTAs of up to 42 KB each must be resident per SM: ask for exactly that much shared memory
+             * (percent of 228 KB; the rest stays L1, which the stack frames of the PHASE calls live in) */
             static const cudaError_t carve = cudaFuncSetAttribute(pair_kernel_refill<P1, P2>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                                  (int)cudaSharedmemCarveoutMaxShared);
+                                                                  (int)((100 * (kMinBlocks * (smem + 1024)) + 228 * 1024 - 1) / (228 * 1024)));
             if (carve != cudaSuccess) return carve;
             pair_kernel_refill<P1, P2><<<(unsigned)blocks, kThreads, smem, stream>>>(a);
             return cudaGetLastError();

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the lane-refill kernels on one GPU (writes gpurun_out/ab2_*.log).  Usage: bash tools/ab_refill.sh
 mkdir -p gpurun_out
-B="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-altro --no-jacobian --no-coherent"
+B="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-altro --no-jacobian --no-coherent --no-sizes --no-parity-sample"
 run() { name=$1; shift; echo "== $name"; ( timeout 180 env "$@" $B $EXTRA_ARGS > gpurun_out/ab2_$name.log 2> gpurun_out/ab2_$name.err; echo "rc=$?" ) ; python - <<PY
 import json
 try:
