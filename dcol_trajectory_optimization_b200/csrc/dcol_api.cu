@@ -121,9 +121,13 @@ struct dcol_shape_table {
     double* scene_obs_pose = nullptr;
     int32_t* scene_obs_shape = nullptr;
     int64_t scene_obs_cap = 0;
+    /* what plans[0] / plans[1] currently describe when a scene call built them: (victim, poses per chunk, obstacle shapes);
+     * a caller that evaluates the same scene again (every AL-iLQR pass) then skips the counting sort and its host wait */
+    std::vector<int32_t> scene_key[2];
 };
 
 struct dcol_plan {
+    int64_t capacity_or_size() const { return capacity > B ? capacity : B; }
     const dcol_shape_table* table; /* borrowed: the table must outlive every solve / refine of this plan ...   */
     int device;                    /* ... but not its destruction: the plan remembers its device              */
     int64_t B, capacity;
@@ -140,6 +144,9 @@ struct dcol_plan {
     int32_t* d_gstart = nullptr;   /* [n_groups + 1] first plan position of every group */
     int32_t* d_bins = nullptr;     /* [2][n_groups * kRefineBins] histogram, cursors       */
     int32_t refine_groups = -1;    /* group count d_gstart / d_bins were sized for          */
+    /* lane-refill path: scratch records (allocated by the first solve that takes the path) */
+    mutable double* d_state = nullptr;
+    mutable int64_t state_stride = 0, state_pairs = 0, state_groups = 0;
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -625,6 +632,7 @@ void dcol_plan_destroy(dcol_plan* P)
     cudaFree(P->d_gstart);
     cudaFree(P->d_bins);
     cudaFree(P->d_counts);
+    cudaFree(P->d_state);
     if (P->h_mapped) cudaFreeHost(P->h_mapped);
     delete P;
 }
@@ -747,6 +755,28 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
         DCOL_CUDA(cudaEventRecord(T->fork_ev, stream));
         for (int i = 0; i < n_side; ++i) DCOL_CUDA(cudaStreamWaitEvent(T->side[i], T->fork_ev, 0));
     }
+    /* lane-refill path (DCOL_LANE_REFILL, or the library default): scratch records for the pairs of this plan */
+    double* d_state = nullptr;
+    int64_t state_stride = 0;
+    if (!d_jac && !(flags & DCOL_ONE_PAIR_PER_THREAD) && ((flags & DCOL_LANE_REFILL) || refill_enabled())) {
+        int words = 0;
+        for (const Group& g : P->groups)
+            if (g.supported || (flags & DCOL_FIX_CASE4)) words = std::max(words, state_words(T->cls[g.i1], T->cls[g.i2]));
+        if (words > 0) {
+            if (P->state_stride < words || P->state_pairs < P->B || P->state_groups < (int64_t)P->groups.size()) {
+                cudaFree(P->d_state);
+                P->d_state = nullptr;
+                P->state_stride = P->state_pairs = P->state_groups = 0;
+                /* every group's records start on a block boundary: 32 spare records per group */
+                DCOL_CUDA(cudaMalloc(&P->d_state, sizeof(double) * (size_t)words * (size_t)(P->capacity_or_size() + 32 * (int64_t)P->groups.size())));
+                P->state_stride = words;
+                P->state_pairs = P->capacity_or_size();
+                P->state_groups = (int64_t)P->groups.size();
+            }
+            d_state = P->d_state;
+            state_stride = P->state_stride;
+        }
+    }
     /* largest groups first: the long grids start early, the short ones fill the tail */
     std::vector<int> order(n_groups);
     for (int i = 0; i < n_groups; ++i) order[i] = i;
@@ -759,6 +789,9 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
                         d_alpha, d_contact, d_grad, d_iters, d_status, nullptr, n_dest, record_offset, {} };
         for (int d = 0; d < n_dest; ++d) a.dest[d] = dest[d];
         a.jac = d_jac;
+        /* group order[oi]'s records: after all the pairs of the groups before it in plan order, plus 32 spare per group */
+        a.state = d_state ? d_state + (g.first + 32 * (int64_t)order[oi]) * state_stride : nullptr;
+        a.state_stride = state_stride;
         cudaError_t e;
         if (!g.supported && !(flags & DCOL_FIX_CASE4)) {
             fill_unsupported<<<(unsigned)((g.count + 255) / 256), 256, 0, st>>>(a);
@@ -793,6 +826,7 @@ static int host_pipeline_setup(dcol_shape_table* T, int64_t chunk)
         S.release();
         dcol_plan_destroy(T->plans[i]);
         T->plans[i] = nullptr;
+        T->scene_key[i].clear();
         cudaError_t e = cudaMalloc(&S.idx1, sizeof(int32_t) * chunk);
         if (e == cudaSuccess) e = cudaMalloc(&S.idx2, sizeof(int32_t) * chunk);
         if (e == cudaSuccess) e = cudaMalloc(&S.iters, sizeof(int32_t) * chunk);
@@ -838,6 +872,8 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
     if (int rc0 = host_pipeline_setup(T, chunk)) return rc0;
+    T->scene_key[0].clear(); /* this call rebuilds both cached plans */
+    T->scene_key[1].clear();
     /* Four streams: copy-in, plan (counting sort), solve, copy-out.  The only host wait per chunk is for
      * that chunk's own histogram, so chunk i+1 is copied in and planned while chunk i is being solved and
      * chunk i-1 is being copied out. */
@@ -936,7 +972,8 @@ int dcol_proximity_scene_host(const dcol_shape_table* T_, int32_t victim_shape, 
     cudaStream_t s_in = T->streams[0], s_run = T->streams[2], s_out = T->streams[3];
     const uint32_t solve_flags = flags | (grad1 ? (uint32_t)(DCOL_WANT_GRAD | DCOL_WANT_GRAD1) : 0u);
     int rc = 0;
-    int64_t planned[2] = { -1, -1 }; /* pair count plans[0] (full chunks) / plans[1] (the last, shorter chunk) were built for */
+    /* plans[0] serves the full chunks, plans[1] the last, shorter one; each is rebuilt only when its key changes */
+    std::vector<int32_t> key_obs(obstacle_shape, obstacle_shape + n_obs);
     const int64_t n_chunks = (M + Mc - 1) / Mc;
     for (int64_t ci = 0; ci < n_chunks && rc == 0; ++ci) {
         const int slot = (int)(ci & 1);
@@ -954,16 +991,23 @@ int dcol_proximity_scene_host(const dcol_shape_table* T_, int32_t victim_shape, 
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_in[slot], s_in));
         DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
         const int which = (mc == Mc) ? 0 : 1;
-        const bool need_plan = planned[which] != n;
+        std::vector<int32_t> key;
+        key.reserve(n_obs + 3);
+        key.push_back(victim_shape);
+        key.push_back((int32_t)mc);
+        key.push_back(n_obs);
+        key.insert(key.end(), key_obs.begin(), key_obs.end());
+        const bool need_plan = T->scene_key[which] != key;
         scene_expand<<<(unsigned)((6 * n + 255) / 256), 256, 0, s_run>>>(victim_shape, T->scene_obs_shape, T->scene_vic[slot],
                                                                         T->scene_obs_pose, n, n_obs, need_plan ? S.idx1 : nullptr,
                                                                         S.idx2, S.pose1, S.pose2);
         DCOL_CUDA_BREAK(cudaGetLastError());
         dcol_plan* P = T->plans[which];
         if (need_plan) {
+            T->scene_key[which].clear();
             rc = plan_build(P, S.idx1, S.idx2, n, s_run);
             if (rc) break;
-            planned[which] = n;
+            T->scene_key[which] = key;
         }
         rc = dcol_proximity_batch_device(P, S.pose1, S.pose2, tol, max_iter, solve_flags, S.alpha, nullptr, grad1 ? S.grad : nullptr,
                                          S.iters, S.status, s_run);

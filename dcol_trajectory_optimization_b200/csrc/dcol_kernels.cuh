@@ -54,7 +54,9 @@ struct BatchArgs {
     double* dest[DCOL_MAX_DEST];
     double* jac; /* [B][4][12] solution Jacobian (jacobian kernels only, otherwise null) */
     int32_t ahead; /* threads of one resident wave (SMs x CTAs/SM x kThreads): L2 prefetch distance, 0 = off */
-    int32_t per_warp; /* lane-refill kernel: plan positions owned by one warp */
+    int32_t per_warp; /* lane-refill path: records owned by one warp of trip_kernel */
+    double* state;    /* lane-refill path: this group's scratch records (blocks of 32 pairs x StateLayout::NW doubles) */
+    int64_t state_stride; /* doubles per pair the scratch was sized for */
 };
 
 /* one pair with the mu trace and the world-frame (x, s, z): the debug entry point */
@@ -209,27 +211,32 @@ __global__ void __launch_bounds__(kThreads, JAC ? 1 : kMinBlocks) pair_kernel(co
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Lane-refill kernel.  pair_kernel above gives a thread ONE pair, so a warp runs until its slowest pair converges:
- * per-pair iteration counts have a long right tail (config 4: mean 8.1, mean of the per-warp maximum 11.2) and
- * 22-26 of 32 lanes are active on average (profiles/r01_ncu_final_8kernels.md).  Iteration counts cannot be
- * predicted from the geometry (sorting by mu_0, mu_1 or alpha moves lane efficiency from 0.72 to 0.74), so the
- * lanes are kept busy dynamically instead:
+ * Lane-refill path: three kernels per group instead of one.
  *
- *   - a warp owns a contiguous chunk of plan positions (per_warp pairs) and a pool of 32 state slots in shared memory;
- *   - PHASE (convergent, all 32 lanes): lane j runs the epilogue (alpha, contact point, gradient, stores) of the
- *     finished pair parked in slot j, then initialises a new pair (pose -> working frame, initial point, NT scaling of
- *     iteration 0) and parks its loop-carried state in slot j as FRESH;
- *   - TRIP (all lanes that hold a pair): one Newton step + the scaling / convergence test of the next iterate;
- *   - a lane whose pair has finished swaps its state with a FRESH slot field by field (the slot becomes DONE) and goes
- *     on with the new pair in the same trip loop; when no FRESH slot is left the next PHASE runs.
+ * pair_kernel above gives a thread ONE pair, so a warp runs until its slowest pair converges: per-pair iteration counts
+ * have a long right tail (config 4: mean 8.1, mean of the per-warp maximum 11.2) and 22-26 of 32 lanes are active on
+ * average (profiles/r01_ncu_final_8kernels.md).  Iteration counts cannot be predicted from the geometry (sorting by
+ * mu_0, mu_1 or alpha moves lane efficiency from 0.72 to 0.74), so the lanes are kept busy dynamically:
  *
- * Lanes of a warp are therefore at different iterations of different pairs; initialisation and epilogue still run
- * 32 pairs at a time.  Per-pair arithmetic is the same sequence of operations as Solver::solve (bit-identical
- * results).  Fixed-size classes only (a slot holds the whole loop-carried state: 48-74 doubles); runtime-face-count
- * classes, the debug trace and the Jacobian kernels use pair_kernel. */
+ *   init_kernel   one thread per pair: pose -> working frame, initial point, NT scaling and tests of iteration 0; the
+ *                 pair's loop state goes to a record of NW doubles in a scratch buffer (plan order);
+ *   trip_kernel   a warp owns a contiguous chunk of records; every lane holds one pair and all lanes run the same
+ *                 iteration body (scaling + tests, one Newton step); a lane whose pair has finished writes its result
+ *                 (x, z, iteration count, status) back into the pair's record and loads the next record of the chunk,
+ *                 so the lanes of a warp are at different iterations of different pairs and stay busy until the chunk
+ *                 runs out;
+ *   finish_kernel one thread per pair: alpha, contact point, gradient and the stores (arrays or records) from the
+ *                 record's final (x, z).
+ *
+ * Each kernel is as small as its job (the iteration body alone is ~20 KB of code: warps of an SM that are at different
+ * points of it still share the instruction cache, which a single kernel holding initialisation, iteration and epilogue
+ * for desynchronised warps does not: measured, profiles/r02_lane_refill_history.md).  The price is the record traffic,
+ * ~1.3 KB per pair against 212 B of inputs and outputs, at 15 % of the HBM bandwidth.  Per-pair arithmetic is the same
+ * sequence of operations as Solver::solve.  Fixed-size classes only; runtime-face-count classes, the debug trace and the
+ * Jacobian kernels use pair_kernel. */
 
 template <class S>
-struct RefillLayout {
+struct StateLayout {
     typedef typename S::F1 F1;
     typedef typename S::F2 F2;
     static constexpr int N = S::N;
@@ -250,12 +257,13 @@ struct RefillLayout {
     static constexpr int SC2 = WH2 + F2::Q;
     static constexpr int POSE = SC2 + (F2::Q > 0 ? 3 : 0); /* Qp[9], rp[3] of the primitive that is not the frame */
     static constexpr int SZ = POSE + 12;
-    static constexpr int META = SZ + 1; /* plan position | iteration << 32 | status << 40 */
-    static constexpr int NW = META + 1;
-    static_assert(NW >= kRecordWords + 1, "the record staging area is overlaid on the pool");
+    static constexpr int META = SZ + 1; /* iteration count | status << 8 | finished << 16 */
+    static constexpr int POSES = META + 1; /* the pair's two input poses (12 doubles): init_kernel gathers them through the
+                                              plan's permutation once, finish_kernel reads them back coalesced */
+    static constexpr int NW = POSES + 12;
 };
 
-/* f(offset, value&, part_of_the_finished_state) over every loop-carried field of one block */
+/* f(offset, value&, part_of_the_finished_state) over every field of one block that the iteration carries or needs */
 template <class P, class F>
 __device__ __forceinline__ void visit_block(Block<P>& B, int so, int zo, int ri, int sq, int zq, int wh, int sc, F&& f)
 {
@@ -280,7 +288,7 @@ __device__ __forceinline__ void visit_block(Block<P>& B, int so, int zo, int ri,
 template <class S, class F>
 __device__ __forceinline__ void visit_state(S& sv, double& sz, F&& f)
 {
-    typedef RefillLayout<S> Lay;
+    typedef StateLayout<S> Lay;
 #pragma unroll
     for (int j = 0; j < S::N; ++j) f(Lay::X + j, sv.x[j], true);
     visit_block(sv.b1, Lay::SO1, Lay::ZO1, Lay::RI1, Lay::SQ1, Lay::ZQ1, Lay::WH1, Lay::SC1, f);
@@ -303,304 +311,226 @@ __device__ __forceinline__ void visit_state(S& sv, double& sz, F&& f)
     f(Lay::SZ, sz, false);
 }
 
-__device__ __forceinline__ double pack_meta(int64_t pos, int it, int status)
+/* Records are stored in blocks of 32 pairs, field-major inside a block: field f of the pair at position pos of its group
+ * lives at (pos / 32 * NW + f) * 32 + pos % 32, so that the one-thread-per-pair kernels (init, finish) read and write
+ * whole 256-byte rows per instruction; the refilling lanes of trip_kernel take consecutive positions and share sectors. */
+template <int NW>
+__device__ __forceinline__ int64_t record_base(int64_t pos)
 {
-    return __longlong_as_double((long long)(uint32_t)pos | ((long long)(it & 0xff) << 32) | ((long long)(status & 0xff) << 40));
-}
-/* position of the (r + 1)-th set bit of m (r < popc(m)) */
-__device__ __forceinline__ int nth_set_bit(unsigned m, int r)
-{
-    int base = 0;
-#pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const unsigned lo = m & ((1u << w) - 1u);
-        const int c = __popc(lo);
-        if (r >= c) {
-            r -= c;
-            m >>= w;
-            base += w;
-        } else {
-            m = lo;
-        }
-    }
-    return base;
+    return (pos >> 5) * (int64_t)(32 * NW) + (pos & 31);
 }
 
-#ifndef DCOL_PHASE_ATTR
-#define DCOL_PHASE_ATTR __noinline__
-#endif
+__device__ __forceinline__ double pack_meta(int iters, int status, bool finished)
+{
+    return __longlong_as_double((long long)(iters & 0xff) | ((long long)(status & 0xff) << 8) | ((long long)(finished ? 1 : 0) << 16));
+}
 
-/* PHASE: epilogue of the DONE slots, then initialisation of new pairs into the (then all free) slots.  Lane j works on
- * slot j.  Precondition: no FRESH slot.  Its own function so that the trip loop's live state is saved around the call
- * instead of competing with the initialisation for registers. */
-struct SlotMasks {
-    unsigned fresh, done;
-};
+constexpr int kServiceThreads = 128; /* init / finish kernels: plain one-thread-per-pair kernels */
+
 template <class P1, class P2>
-__device__ DCOL_PHASE_ATTR SlotMasks refill_phase(const GroupArgs<P1, P2>& a, double* pool, unsigned done, int32_t next,
-                                                  int32_t end)
+__global__ void __launch_bounds__(kServiceThreads) init_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
 {
     typedef Solver<P1, P2> S;
-    typedef RefillLayout<S> Lay;
+    typedef StateLayout<S> Lay;
+    const int64_t t = (int64_t)blockIdx.x * kServiceThreads + threadIdx.x;
+    if (t >= a.b.count) return;
+    const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + t] : a.b.first + t;
+    double pose1[6], pose2[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
+        pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
+    }
+    S sv;
+    double sz = 0.0;
+    int32_t iters = 0;
+    int st = sv.init_point(a.c1, a.c2, pose1, pose2);
+    if (st == 0) st = sv.scale_and_check(a.c1, a.c2, a.b.tol, 0, iters, sz, nullptr);
+    double* rec = a.b.state + record_base<Lay::NW>(t);
+    visit_state(sv, sz, [&](int off, double& v, bool) { rec[32 * off] = v; });
+    rec[32 * Lay::META] = pack_meta(iters, st == S::kContinue ? 0 : st, st != S::kContinue);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        rec[32 * (Lay::POSES + j)] = pose1[j];
+        rec[32 * (Lay::POSES + 6 + j)] = pose2[j];
+    }
+}
+
+template <class P1, class P2>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) trip_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
+{
+    typedef Solver<P1, P2> S;
+    typedef StateLayout<S> Lay;
     const int lane = threadIdx.x & 31;
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    const bool records = a.b.n_dest > 0;
-    const bool want_grad = records || (a.b.flags & DCOL_WANT_GRAD) != 0;
-    if (done) {
-        const bool mine = (done >> lane) & 1u;
-        S sv;
-        double sz_unused = 0.0;
-        long long meta = 0;
-        if (mine) {
-            visit_state(sv, sz_unused, [&](int off, double& v, bool fin) {
-                if (fin) v = pool[off * 32 + lane];
-            });
-            meta = __double_as_longlong(pool[Lay::META * 32 + lane]);
-        }
-        __syncwarp(); /* every lane has its finished state in registers: the pool may now be reused as staging */
-        const int64_t pos = (int64_t)(uint32_t)meta;
-        const int iters = (int)((meta >> 32) & 0xff), st = (int)((meta >> 40) & 0xff);
-        double* stage = pool;                                              /* [32][kRecordWords] */
-        int32_t* stage_pos = reinterpret_cast<int32_t*>(pool + 32 * kRecordWords); /* [32] */
-        if (mine) {
-            const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos] : a.b.first + pos;
-            double pose1[6], pose2[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
-                pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
-            }
-            const double alpha = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
-            if (a.b.flags & DCOL_WANT_CONTACT) {
-                double cp[3] = { nan, nan, nan };
-                if (st == DCOL_STATUS_OK) sv.contact_point(a.c1, a.c2, pose1, pose2, cp);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = cp[j]; /* proximity.py:52 */
-            }
-            double g[12];
-            if (want_grad) {
-                if (st == DCOL_STATUS_OK) {
-                    sv.gradient(a.c1, a.c2, pose1, pose2, g, !(a.b.flags & DCOL_WANT_GRAD1));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) g[j] = nan;
-                }
-            }
-            if (!records) {
-                a.b.status[k] = st;
-                a.b.iters[k] = iters;
-                a.b.alpha[k] = alpha;
-                if (want_grad) {
-                    if (a.b.flags & DCOL_WANT_GRAD1) {
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) a.b.grad[6 * k + j] = g[j];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
-                    }
-                }
-            } else {
-                double* rec = stage + lane * kRecordWords;
-                rec[0] = alpha;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) rec[1 + j] = g[j];
-                rec[13] = __longlong_as_double((long long)(uint32_t)iters | ((long long)st << 32));
-                stage_pos[lane] = (int32_t)pos;
-            }
-        }
-        if (records) {
-            /* a record is 112 contiguous bytes at its plan position: seven consecutive lanes write one record with
-             * 16-byte stores (whole sectors; full-size NVLink packets for peer / multicast destinations) */
-            __syncwarp();
-            const int64_t base = a.b.record_offset + a.b.first;
-            for (int c = lane; c < 32 * (kRecordWords / 2); c += 32) {
-                const int r = c / (kRecordWords / 2), piece = c - r * (kRecordWords / 2);
-                if (!((done >> r) & 1u)) continue;
-                const int64_t off = kRecordWords * (base + stage_pos[r]) + 2 * piece;
-                if (a.b.flags & DCOL_DEST_MULTICAST) {
-                    const float4 v = *reinterpret_cast<const float4*>(stage + r * kRecordWords + 2 * piece);
-                    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.b.dest[0] + off), "f"(v.x),
-                                 "f"(v.y), "f"(v.z), "f"(v.w)
-                                 : "memory");
-                } else {
-                    const double2 v = *reinterpret_cast<const double2*>(stage + r * kRecordWords + 2 * piece);
-                    for (int d = 0; d < a.b.n_dest; ++d) *reinterpret_cast<double2*>(a.b.dest[d] + off) = v;
-                }
-            }
-        }
-        __syncwarp();
-        done = 0;
-    }
-    /* initialisation: lane j takes plan position next + j into slot j */
-    const int32_t n_new = end - next < 32 ? end - next : 32;
-    int st = 0;
-    bool is_new = false;
-    if (lane < n_new) {
-        is_new = true;
-        const int64_t pos = (int64_t)next + lane;
-        const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos] : a.b.first + pos;
-        if (pos + 32 < end) { /* the pair this lane initialises in the NEXT phase: pull its poses into L2 now */
-            const int64_t kn = a.b.perm ? (int64_t)a.b.perm[a.b.first + pos + 32] : a.b.first + pos + 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose1 + 6 * kn));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose1 + 6 * kn + 5));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose2 + 6 * kn));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.b.pose2 + 6 * kn + 5));
-        }
-        double pose1[6], pose2[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            pose1[j] = __ldg(a.b.pose1 + 6 * k + j);
-            pose2[j] = __ldg(a.b.pose2 + 6 * k + j);
-        }
-        S sv;
-        double sz = 0.0;
-        int32_t iters = 0;
-        st = sv.init_point(a.c1, a.c2, pose1, pose2);
-        if (st == 0) st = sv.scale_and_check(a.c1, a.c2, a.b.tol, 0, iters, sz, nullptr);
-        /* park the whole state (a finished pair only needs its x and z, which are among the fields) */
-        visit_state(sv, sz, [&](int off, double& v, bool) { pool[off * 32 + lane] = v; });
-        pool[Lay::META * 32 + lane] = pack_meta(pos, iters, st == S::kContinue ? 0 : st);
-    }
-    SlotMasks m;
-    m.fresh = __ballot_sync(0xffffffffu, is_new && st == S::kContinue);
-    m.done = __ballot_sync(0xffffffffu, is_new && st != S::kContinue);
-    __syncwarp();
-    return m;
-}
-
-/* Control structure: an OUTER loop with one PHASE (a call) per turn, and inside it a call-free INNER loop of trips that
- * runs until the pool has no FRESH slot left for a lane that needs one.  The inner loop's state (x, s, z, the relative
- * pose; ~50-70 doubles per lane) is written to a local array when the inner loop is left and read back when it is
- * entered again, once per generation of 32 pairs, so that nothing but a few integers is live across the call.  (With the
- * call inside the trip loop ptxas kept ~25 doubles of loop state in the stack frame and moved them on EVERY trip; local
- * memory then misses L1, most of which is carved out as shared memory for the pool, and the stores go to L2.) */
-template <class P1, class P2>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel_refill(const __grid_constant__ GroupArgs<P1, P2> a)
-{
-    typedef Solver<P1, P2> S;
-    typedef RefillLayout<S> Lay;
-    extern __shared__ __align__(16) double pool_all[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double* pool = pool_all + w * (32 * Lay::NW);
-    const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + w;
+    const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     if (warp_id * (int64_t)a.b.per_warp >= a.b.count) return;
     int32_t next = (int32_t)(warp_id * a.b.per_warp); /* a group holds fewer than 2^31 pairs (dcol_plan_create) */
     const int32_t end = (int64_t)next + a.b.per_warp < a.b.count ? next + a.b.per_warp : (int32_t)a.b.count;
     const unsigned lt = (1u << lane) - 1u;
+    double* const base = a.b.state; /* this group's records */
 
-    double park[Lay::NW]; /* this lane's pair while a PHASE runs */
+    S sv;
+    double sz = 0.0;
     bool has = false, fin = false;
     int it = 0, status = 0;
     int32_t iters = 0, pos = 0;
-    unsigned fresh = 0, done = 0; /* slot states, warp-uniform; a slot in neither set is free */
-
     for (;;) {
-        /* ---- PHASE: epilogue of the DONE slots, initialisation of up to 32 new pairs ---- */
-        {
-            const SlotMasks m = refill_phase<P1, P2>(a, pool, done, next, end);
-            fresh = m.fresh;
-            done = m.done;
-            next += end - next < 32 ? end - next : 32;
-        }
-        if (fresh == 0 && !__any_sync(0xffffffffu, has)) {
-            if (next < end) continue; /* every new pair ended inside its initialisation: next generation */
-            if (done) (void)refill_phase<P1, P2>(a, pool, done, next, end);
-            return;
-        }
-        /* ---- trips, until a lane needs a FRESH slot and there is none ---- */
-        S sv;
-        double sz = 0.0;
-        if (has) visit_state(sv, sz, [&](int off, double& v, bool) { v = park[off]; });
-        bool scaled = true; /* a parked pair was parked AFTER the scaling / tests of its current iterate */
-        for (;;) {
-            /* top of an iteration for every lane that holds a pair: NT scaling of its iterate, mu, the convergence test.
-             * (The scaling is not carried around the loop: only x, s, z and the relative pose are, as in Solver::solve;
-             * a pair taken from a FRESH slot below brings the scaling of its iteration 0 with it.) */
-            if (!scaled && has && !fin) {
-                if (it >= a.b.max_iter) {
+        /* scaling and tests of the current iterate, for every lane that went through a Newton step (a record that was
+         * just loaded brings the scaling of its iteration 0 with it) */
+        if (has && !fin) {
+            if (it >= a.b.max_iter) {
+                fin = true;
+                status = sv.cap_status(a.b.max_iter, iters);
+            } else if (it > 0) {
+                const int st = sv.scale_and_check(a.c1, a.c2, a.b.tol, it, iters, sz, nullptr);
+                if (st != S::kContinue) {
                     fin = true;
-                    status = sv.cap_status(a.b.max_iter, iters);
-                } else {
-                    const int st = sv.scale_and_check(a.c1, a.c2, a.b.tol, it, iters, sz, nullptr);
-                    if (st != S::kContinue) {
-                        fin = true;
-                        status = st;
-                    }
+                    status = st;
                 }
             }
-            scaled = false;
-            /* settle: finished lanes park their result, lanes without a pair take a FRESH state */
-            const unsigned m_fin = __ballot_sync(0xffffffffu, has && fin);
-            const unsigned m_empty = __ballot_sync(0xffffffffu, !has);
-            const int n_fresh = __popc(fresh), n_fin = __popc(m_fin);
-            const unsigned free_slots = ~(fresh | done);
-            const int n_free = __popc(free_slots);
-            int slot = -1, action = 0; /* 1 swap with a FRESH slot, 2 store into a free slot, 3 load a FRESH slot */
+        }
+        /* refill: a finished lane writes (x, z, iterations, status) into its pair's record; it and the lanes without a
+         * pair take the next records of the chunk (those that are already final — the initialisation failed or
+         * converged at the initial point — are skipped) */
+        for (;;) {
+            const unsigned m_need = __ballot_sync(0xffffffffu, !has || fin);
+            if (m_need == 0) break;
             if (has && fin) {
-                const int r = __popc(m_fin & lt);
-                if (r < n_fresh) {
-                    slot = nth_set_bit(fresh, r);
-                    action = 1;
-                } else if (r - n_fresh < n_free) {
-                    slot = nth_set_bit(free_slots, r - n_fresh);
-                    action = 2;
-                }
-            } else if (!has) {
-                const int r = n_fin + __popc(m_empty & lt);
-                if (r < n_fresh) {
-                    slot = nth_set_bit(fresh, r);
-                    action = 3;
-                }
-            }
-            if (action == 1 || action == 3) {
-                const double my_meta = pack_meta(pos, iters, status);
-                const long long meta = __double_as_longlong(pool[Lay::META * 32 + slot]);
-                if (action == 1) {
-                    visit_state(sv, sz, [&](int off, double& v, bool part) {
-                        const double t = pool[off * 32 + slot];
-                        if (part) pool[off * 32 + slot] = v;
-                        v = t;
-                    });
-                    pool[Lay::META * 32 + slot] = my_meta;
-                } else {
-                    visit_state(sv, sz, [&](int off, double& v, bool) { v = pool[off * 32 + slot]; });
-                }
-                pos = (int32_t)(uint32_t)meta;
-                it = 0;
-                has = true;
-                fin = false;
-            } else if (action == 2) {
+                double* rec = base + record_base<Lay::NW>(pos);
                 visit_state(sv, sz, [&](int off, double& v, bool part) {
-                    if (part) pool[off * 32 + slot] = v;
+                    if (part) rec[32 * off] = v;
                 });
-                pool[Lay::META * 32 + slot] = pack_meta(pos, iters, status);
+                rec[32 * Lay::META] = pack_meta(iters, status, true);
                 has = false;
                 fin = false;
             }
-            const unsigned bit = slot >= 0 ? (1u << slot) : 0u;
-            const unsigned to_done = __reduce_or_sync(0xffffffffu, (action == 1 || action == 2) ? bit : 0u);
-            const unsigned to_free = __reduce_or_sync(0xffffffffu, action == 3 ? bit : 0u);
-            fresh &= ~(to_done | to_free);
-            done |= to_done;
-            __syncwarp();
-            const bool holder = __any_sync(0xffffffffu, has && fin);
-            if (fresh == 0 && (holder || next < end)) break;    /* a PHASE is due */
-            if (!__any_sync(0xffffffffu, has)) break;            /* nothing in flight, nothing FRESH, nothing to initialise */
-            /* one Newton step for every lane that holds an unfinished pair */
-            if (has && !fin) {
-                const int st = sv.newton_step(a.c1, a.c2, sz);
-                if (st != 0) {
-                    fin = true;
-                    status = st;
-                    iters = it;
-                } else {
-                    ++it;
+            if (next >= end) break;
+            if (!has) {
+                const int32_t mine = next + __popc(m_need & lt);
+                if (mine < end) {
+                    const double* rec = base + record_base<Lay::NW>(mine);
+                    const long long meta = __double_as_longlong(rec[32 * Lay::META]);
+                    if (!((meta >> 16) & 1)) { /* needs iterations */
+                        visit_state(sv, sz, [&](int off, double& v, bool) { v = rec[32 * off]; });
+                        pos = mine;
+                        it = 0;
+                        has = true;
+                    }
                 }
             }
+            const int n_need = __popc(m_need);
+            next = end - next < n_need ? end : next + n_need;
         }
-        if (has) visit_state(sv, sz, [&](int off, double& v, bool) { park[off] = v; });
-        /* here: a PHASE is due (holders wait for a free slot, or new pairs can be initialised), or everything is finished
-         * and the DONE slots still need their epilogue — both are the next turn's PHASE; the exit test follows it */
+        if (!__any_sync(0xffffffffu, has)) break;
+        if (next + 4 < end) { /* pull the block of records the next refills read towards this SM while the Newton step runs:
+                                 256 bytes per field, lane l fetches the fields l, l + 32, l + 64 */
+            const double* blk = base + record_base<Lay::NW>((next + 4) & ~31);
+#pragma unroll
+            for (int f = 0; f < Lay::NW; f += 32)
+                if (f + lane < Lay::NW) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(blk + 32 * (f + lane)));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(blk + 32 * (f + lane) + 16));
+                }
+        }
+        /* one Newton step for every lane that holds an unfinished pair */
+        if (has && !fin) {
+            const int st = sv.newton_step(a.c1, a.c2, sz);
+            if (st != 0) {
+                fin = true;
+                status = st;
+                iters = it;
+            }
+            ++it;
+        }
+    }
+}
+
+template <class P1, class P2>
+__global__ void __launch_bounds__(kServiceThreads, 4) finish_kernel(const __grid_constant__ GroupArgs<P1, P2> a)
+{
+    typedef Solver<P1, P2> S;
+    typedef StateLayout<S> Lay;
+    const int64_t t = (int64_t)blockIdx.x * kServiceThreads + threadIdx.x;
+    const unsigned lanes = __ballot_sync(0xffffffffu, t < a.b.count);
+    if (t >= a.b.count) return;
+    const int64_t k = a.b.perm ? (int64_t)a.b.perm[a.b.first + t] : a.b.first + t;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool records = a.b.n_dest > 0;
+    const bool want_grad = records || (a.b.flags & DCOL_WANT_GRAD) != 0;
+    S sv;
+    double sz_unused = 0.0;
+    const double* rec = a.b.state + record_base<Lay::NW>(t);
+    double pose1[6], pose2[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        pose1[j] = rec[32 * (Lay::POSES + j)];
+        pose2[j] = rec[32 * (Lay::POSES + 6 + j)];
+    }
+    visit_state(sv, sz_unused, [&](int off, double& v, bool part) {
+        if (part) v = rec[32 * off];
+    });
+    const long long meta = __double_as_longlong(rec[32 * Lay::META]);
+    const int iters = (int)(meta & 0xff), st = (int)((meta >> 8) & 0xff);
+    const double alpha = st == DCOL_STATUS_OK ? sv.x[3] : nan; /* proximity.py:51 */
+    if (a.b.flags & DCOL_WANT_CONTACT) {
+        double cp[3] = { nan, nan, nan };
+        if (st == DCOL_STATUS_OK) sv.contact_point(a.c1, a.c2, pose1, pose2, cp);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a.b.contact[3 * k + j] = cp[j]; /* proximity.py:52 */
+    }
+    double g[12];
+    if (want_grad) {
+        if (st == DCOL_STATUS_OK) {
+            sv.gradient(a.c1, a.c2, pose1, pose2, g, records || !(a.b.flags & DCOL_WANT_GRAD1));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) g[j] = nan;
+        }
+    }
+    if (!records) {
+        a.b.status[k] = st;
+        a.b.iters[k] = iters;
+        a.b.alpha[k] = alpha;
+        if (want_grad) {
+            if (a.b.flags & DCOL_WANT_GRAD1) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a.b.grad[6 * k + j] = g[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) a.b.grad[12 * k + j] = g[j];
+            }
+        }
+        return;
+    }
+    /* record mode, as in pair_kernel: a warp's records are contiguous in plan order; transposed through shared memory
+     * and written with 16-byte stores that cover whole 128-byte lines, once per destination */
+    __shared__ __align__(16) double stage_all[(kServiceThreads / 32) * 32 * kRecordWords];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* stage_w = stage_all + w * (32 * kRecordWords);
+    double* mine = stage_w + lane * kRecordWords;
+    mine[0] = alpha;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) mine[1 + j] = g[j];
+    mine[13] = __longlong_as_double((long long)(uint32_t)iters | ((long long)st << 32));
+    __syncwarp(lanes);
+    const int n_lanes = __popc(lanes);
+    const int n_chunks = n_lanes * (kRecordWords / 2);
+    const int64_t t0 = t - lane;
+    if (a.b.flags & DCOL_DEST_MULTICAST) {
+        const float4* src4 = reinterpret_cast<const float4*>(stage_w);
+        float4* dst = reinterpret_cast<float4*>(a.b.dest[0] + kRecordWords * (a.b.record_offset + a.b.first + t0));
+        for (int c = lane; c < n_chunks; c += n_lanes) {
+            const float4 v = src4[c];
+            asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x), "f"(v.y), "f"(v.z),
+                         "f"(v.w)
+                         : "memory");
+        }
+    } else {
+        const double2* src = reinterpret_cast<const double2*>(stage_w);
+        for (int d = 0; d < a.b.n_dest; ++d) {
+            double2* dst = reinterpret_cast<double2*>(a.b.dest[d] + kRecordWords * (a.b.record_offset + a.b.first + t0));
+            for (int c = lane; c < n_chunks; c += n_lanes) dst[c] = src[c];
+        }
     }
 }
 
@@ -625,6 +555,29 @@ inline int resident_wave_threads()
     return sms * kMinBlocks * kThreads;
 }
 
+/* doubles per scratch record of the lane-refill path for a pair of classes (0: the pair does not use the path) */
+template <int C1, int C2>
+constexpr int state_words_of()
+{
+    typedef typename ClassPrim<C1>::type P1;
+    typedef typename ClassPrim<C2>::type P2;
+    if constexpr (P1::dyn || P2::dyn) return 0;
+    else return StateLayout<Solver<P1, P2>>::NW;
+}
+struct StateWordsFn {
+    int words = 0;
+    template <int A1, int A2>
+    void operator()()
+    {
+        words = state_words_of<A1, A2>();
+    }
+};
+inline int state_words(int c1, int c2)
+{
+    StateWordsFn f;
+    return dispatch_classes(c1, c2, f) ? f.words : 0;
+}
+
 /* lane-refill kernels as the default path: environment DCOL_REFILL=0/1 (A/B switch), else DCOL_REFILL_DEFAULT */
 #ifndef DCOL_REFILL_DEFAULT
 #define DCOL_REFILL_DEFAULT 0
@@ -645,7 +598,9 @@ inline int32_t refill_pairs_per_warp(int64_t count)
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             sms = 148;
     }
-    int64_t gen = forced > 0 ? forced : count / (32LL * sms * kMinBlocks * (kThreads / 32));
+    /* about 0.7 resident waves of trip_kernel warps per group launch (several groups run concurrently on side streams):
+     * measured best on config 4 (8 generations at 209,715 pairs per group) */
+    int64_t gen = forced > 0 ? forced : (int64_t)((double)count / (32.0 * sms * kMinBlocks * (kThreads / 32) * 0.7) + 0.5);
     gen = gen < 1 ? 1 : (gen > 16 ? 16 : gen);
     if (forced > 0) gen = forced;
     return (int32_t)(32 * gen);
@@ -662,18 +617,16 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
     a.b = g.args;
     if (g.args.count <= 0) return cudaSuccess;
     if constexpr (!JAC && !P1::dyn && !P2::dyn) {
-        if (!g.args.trace && !(g.args.flags & DCOL_ONE_PAIR_PER_THREAD) && ((g.args.flags & DCOL_LANE_REFILL) || refill_enabled())) {
-            typedef RefillLayout<Solver<P1, P2>> Lay;
+        if (!g.args.trace && g.args.state && !(g.args.flags & DCOL_ONE_PAIR_PER_THREAD) &&
+            ((g.args.flags & DCOL_LANE_REFILL) || refill_enabled())) {
+            typedef StateLayout<Solver<P1, P2>> Lay;
+            if (Lay::NW > g.args.state_stride) return cudaErrorInvalidValue;
             a.b.per_warp = refill_pairs_per_warp(g.args.count);
             const int64_t warps = (g.args.count + a.b.per_warp - 1) / a.b.per_warp;
-            const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
-            const size_t smem = sizeof(double) * (kThreads / 32) * 32 * Lay::NW;
-            /* kMinBlocks CTAs of up to 42 KB each must be resident per SM: ask for exactly that much shared memory
-             * (percent of 228 KB; the rest stays L1, which the stack frames of the PHASE calls live in) */
-            static const cudaError_t carve = cudaFuncSetAttribute(pair_kernel_refill<P1, P2>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                                  (int)((100 * (kMinBlocks * (smem + 1024)) + 228 * 1024 - 1) / (228 * 1024)));
-            if (carve != cudaSuccess) return carve;
-            pair_kernel_refill<P1, P2><<<(unsigned)blocks, kThreads, smem, stream>>>(a);
+            const unsigned service_blocks = (unsigned)((g.args.count + kServiceThreads - 1) / kServiceThreads);
+            init_kernel<P1, P2><<<service_blocks, kServiceThreads, 0, stream>>>(a);
+            trip_kernel<P1, P2><<<(unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32)), kThreads, 0, stream>>>(a);
+            finish_kernel<P1, P2><<<service_blocks, kServiceThreads, 0, stream>>>(a);
             return cudaGetLastError();
         }
     }

@@ -452,8 +452,8 @@ def test_lane_refill_matches_one_pair_per_thread(dcol, n_pairs):
         # contact point and gradient: to rounding for the bulk; pairs with a non-unique contact point (parallel faces,
         # about 1 in 1e5) move under ANY change of rounding, in the reference's own arithmetic too
         assert not bool(a.grad[ok].isnan().any()) and not bool(b.grad[ok].isnan().any())
-        assert float(b.grad[ok].abs().amax(dim=1).min()) > 0.0
-        gerr = (a.grad[ok] - b.grad[ok]).abs().amax(dim=1) / b.grad[ok].abs().amax(dim=1)
+        # (at tol = 5 many pairs stop at the initial point, where the dual of a whole primitive can be exactly zero)
+        gerr = (a.grad[ok] - b.grad[ok]).abs().amax(dim=1) / b.grad[ok].abs().amax(dim=1).clamp(min=1e-300)
         cerr = (a.contact[ok] - b.contact[ok]).abs().amax(dim=1) / b.contact[ok].abs().amax(dim=1).clamp(min=1.0)
         if int(ok.sum()) > 0:
             assert float(gerr.quantile(0.999)) < 1e-8 and float(gerr.max()) < 1e-3, (float(gerr.quantile(0.999)), float(gerr.max()))
