@@ -143,6 +143,7 @@ class Plan:
         import torch
         if not (iters.is_cuda and iters.dtype == torch.int32 and iters.is_contiguous() and iters.numel() == self.size):
             raise ValueError(f"iters must be a contiguous int32 CUDA tensor of {self.size} elements")
+        self.engine._check_open(self)
         stream = torch.cuda.current_stream(self.engine.device).cuda_stream
         _lib.check(_lib.lib().dcol_plan_refine(self._handle, iters.data_ptr(), stream))
 
@@ -193,8 +194,16 @@ class ProximityEngine:
             pass
 
     # ------------------------------------------------------------------ device buffers
+    def _check_open(self, plan=None):
+        """A plan borrows the engine's shape table: using either after ``close()`` is an error, not undefined behaviour."""
+        if getattr(self, "_table", None) is None:
+            raise RuntimeError("this ProximityEngine has been closed")
+        if plan is not None and (plan.engine is not self or getattr(plan, "_handle", None) is None):
+            raise RuntimeError("the plan is closed or belongs to another engine")
+
     def plan(self, idx1, idx2) -> Plan:
         import torch
+        self._check_open()
         return Plan(self, torch.as_tensor(idx1), torch.as_tensor(idx2))
 
     def solve(self, plan: Plan, pose1, pose2, tol: float = 1e-6, max_iter: int = 50, want_grad: bool = True,
@@ -211,6 +220,7 @@ class ProximityEngine:
         (``DCOL_WANT_GRAD1``: what the reference's callers consume).  ``one_pair_per_thread``: use the kernels
         without lane refill, ``lane_refill``: force the lane-refill kernels (neither: the library's default)."""
         import torch
+        self._check_open(plan)
         B = plan.size
         if grad1 and want_jac:
             raise ValueError("grad1 is not available together with want_jac")
@@ -254,6 +264,7 @@ class ProximityEngine:
         order, to each of the raw device addresses ``dest_ptrs`` (local buffers or peer-GPU buffers mapped with
         CUDA IPC — the all-gather of the results fused into the solve).  Enqueues on the current stream."""
         import torch
+        self._check_open(plan)
         B = plan.size
         for name, t in (("pose1", pose1), ("pose2", pose2)):
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (B, 6)):

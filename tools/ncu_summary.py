@@ -1,5 +1,7 @@
 """Summarise `ncu --set full` reports (read with `ncu -i X.ncu-rep --page raw --csv`) into a markdown
-table for profiles/.  Usage: python tools/ncu_summary.py out.md rep1.ncu-rep [rep2.ncu-rep ...]"""
+table for profiles/.  Usage: python tools/ncu_summary.py out.md rep1.ncu-rep [rep2.ncu-rep ...]
+With --json out.json: also write the DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum of every
+captured launch and their mean) that bench.py reports as roofline.traffic."""
 import csv
 import io
 import subprocess
@@ -26,7 +28,13 @@ COLS = [
 ]
 
 
-def main(out, reps):
+def _bytes(value, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    return float(value.replace(",", "")) * scale
+
+
+def main(out, reps, json_out=None, pairs_per_launch=209715):
+    traffic = []
     lines = ["| kernel | " + " | ".join(c[1] for c in COLS) + " |", "|---|" + "---|" * len(COLS)]
     for rep in reps:
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -35,6 +43,9 @@ def main(out, reps):
         ci = {h: i for i, h in enumerate(hdr)}
         for r in rows[2:]:
             name = r[ci["Kernel Name"]].replace("void ", "").replace("(GroupArgs<T1, T2>)", "")
+            if "dram__bytes_read.sum" in ci and r[ci["dram__bytes_read.sum"]] != "":
+                traffic.append({"kernel": name, "dram_read_bytes": _bytes(r[ci["dram__bytes_read.sum"]], units[ci["dram__bytes_read.sum"]]),
+                                "dram_write_bytes": _bytes(r[ci["dram__bytes_write.sum"]], units[ci["dram__bytes_write.sum"]])})
             cells = []
             for key, _, fmt in COLS:
                 if key not in ci or r[ci[key]] == "":
@@ -49,7 +60,19 @@ def main(out, reps):
             lines.append(f"| `{name}` | " + " | ".join(cells) + " |")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    if json_out and traffic:
+        import json
+        mean = sum(t["dram_read_bytes"] + t["dram_write_bytes"] for t in traffic) / len(traffic)
+        json.dump({"mean_dram_bytes_per_launch": mean, "pairs_per_launch": pairs_per_launch, "launches": len(traffic),
+                   "per_launch": traffic, "source": ", ".join(reps) + " (ncu --set full --clock-control none)"},
+                  open(json_out, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2:])
+    args = sys.argv[1:]
+    jo = None
+    if "--json" in args:
+        i = args.index("--json")
+        jo = args[i + 1]
+        del args[i:i + 2]
+    main(args[0], args[1:], jo)
