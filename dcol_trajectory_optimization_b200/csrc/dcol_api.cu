@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -110,11 +111,18 @@ struct dcol_shape_table {
     cudaEvent_t fork_ev = nullptr, join_ev[kSide] = {};
     /* host entry point state */
     std::mutex mu;
-    HostScratch scratch[2];
-    dcol_plan* plans[2] = { nullptr, nullptr };
+    /* chunk slots of the host pipelines: the pair-list entry point rotates through up to kSlots of them, so that the
+     * copy-in and the counting sort of later chunks (and the host thread that waits for their histograms) run ahead of
+     * the solve instead of being gated by the chunk before last; the scene entry point uses the first two */
+    static constexpr int kSlots = 4;
+    HostScratch scratch[kSlots];
+    dcol_plan* plans[kSlots] = {};
     cudaStream_t streams[4] = { nullptr, nullptr, nullptr, nullptr }; /* h2d, plan, solve, d2h */
-    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_plan[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr },
-                ev_out[2] = { nullptr, nullptr };
+    /* pair-list entry point: one solve stream per slot.  A solve forks from / joins into its own stream, so consecutive
+     * chunks have no barrier between them: each side stream starts chunk i+1's kernels right behind its kernels of chunk
+     * i (a chunk's 40 small grids leave the SMs half empty at every join otherwise: tools/diag_small_solve.py) */
+    cudaStream_t run[kSlots] = {};
+    cudaEvent_t ev_in[kSlots] = {}, ev_plan[kSlots] = {}, ev_done[kSlots] = {}, ev_out[kSlots] = {};
     /* scene entry point: victim poses of a chunk (two slots), the obstacles of the call */
     double* scene_vic[2] = { nullptr, nullptr };
     int64_t scene_vic_cap = 0;
@@ -509,7 +517,7 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
 {
     if (!T) return;
     DeviceGuard guard_(T->device);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < dcol_shape_table::kSlots; ++i) {
         T->scratch[i].release();
         dcol_plan_destroy(T->plans[i]);
         if (T->ev_in[i]) cudaEventDestroy(T->ev_in[i]);
@@ -523,6 +531,8 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
     cudaFree(T->scene_obs_shape);
     for (int i = 0; i < 4; ++i)
         if (T->streams[i]) cudaStreamDestroy(T->streams[i]);
+    for (int i = 0; i < dcol_shape_table::kSlots; ++i)
+        if (T->run[i]) cudaStreamDestroy(T->run[i]);
     for (int i = 0; i < dcol_shape_table::kSide; ++i) {
         if (T->side[i]) cudaStreamDestroy(T->side[i]);
         if (T->join_ev[i]) cudaEventDestroy(T->join_ev[i]);
@@ -573,6 +583,77 @@ static int plan_build(dcol_plan* P, const int32_t* d_idx1, const int32_t* d_idx2
     memcpy(P->h_mapped, P->h_counts.data(), sizeof(int32_t) * (size_t)nk);
     plan_export_counts<<<(nk + 255) / 256 > 64 ? 64 : (nk + 255) / 256, 256, 0, stream>>>(P->d_mapped, P->d_counts, nk);
     DCOL_CUDA(cudaGetLastError());
+    plan_scatter<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, P->d_counts, P->d_perm);
+    DCOL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* The same grouping when the shape indices are (also) in HOST memory: the histogram is counted by the calling thread,
+ * so nothing waits for the device (on the device the counting kernel only gets CTA slots when the pair kernels of the
+ * chunk before drain — stream priorities do not help against a grid that owns every register — and the host thread
+ * that waited for it could not enqueue the next chunk's copies; measured with DCOL_HOST_TRACE).  Only the scatter
+ * runs on `stream`; it reads the cursors from the plan's mapped buffer when it executes, so the caller must not
+ * rebuild this plan before that has happened (the host entry point waits on the slot's ev_plan). */
+static int plan_build_host_counts(dcol_plan* P, const int32_t* h_idx1, const int32_t* h_idx2, const int32_t* d_idx1,
+                                  const int32_t* d_idx2, int64_t B, cudaStream_t stream)
+{
+    const dcol_shape_table* T = P->table;
+    const int32_t ns = (int32_t)T->shapes.size();
+    const int32_t nk = ns * ns;
+    P->B = B;
+    P->groups.clear();
+    P->n_launches = 0;
+    if (B == 0) return 0;
+    (void)cudaGetLastError();
+    /* four interleaved histograms: consecutive pairs very often share a key (scenes), and one counter would then
+     * serialise on its own store-to-load forwarding */
+    const int lanes = nk <= 65536 ? 4 : 1;
+    std::vector<int32_t>& cnt = P->h_counts;
+    cnt.assign((size_t)nk * lanes + 1, 0);
+    const uint32_t uns = (uint32_t)ns;
+    bool bad = false;
+    int64_t k = 0;
+    if (lanes == 4) {
+        int32_t* c0 = cnt.data();
+        int32_t *c1 = c0 + nk, *c2 = c1 + nk, *c3 = c2 + nk;
+        for (; k + 4 <= B; k += 4) {
+            const uint32_t a0 = (uint32_t)h_idx1[k], b0 = (uint32_t)h_idx2[k], a1 = (uint32_t)h_idx1[k + 1], b1 = (uint32_t)h_idx2[k + 1];
+            const uint32_t a2 = (uint32_t)h_idx1[k + 2], b2 = (uint32_t)h_idx2[k + 2], a3 = (uint32_t)h_idx1[k + 3], b3 = (uint32_t)h_idx2[k + 3];
+            if ((a0 >= uns) | (b0 >= uns) | (a1 >= uns) | (b1 >= uns) | (a2 >= uns) | (b2 >= uns) | (a3 >= uns) | (b3 >= uns)) {
+                bad = true;
+                break;
+            }
+            ++c0[a0 * uns + b0];
+            ++c1[a1 * uns + b1];
+            ++c2[a2 * uns + b2];
+            ++c3[a3 * uns + b3];
+        }
+    }
+    for (; k < B && !bad; ++k) {
+        const uint32_t a = (uint32_t)h_idx1[k], b = (uint32_t)h_idx2[k];
+        if (a >= uns || b >= uns) bad = true;
+        else ++cnt[(size_t)a * uns + b];
+    }
+    if (bad) return fail(DCOL_E_INDEX, "shape index out of range");
+    int64_t off = 0;
+    for (int32_t key = 0; key < nk; ++key) {
+        int32_t c = cnt[key];
+        for (int l = 1; l < lanes; ++l) c += cnt[(size_t)l * nk + key];
+        P->h_mapped[key] = (int32_t)off; /* the scatter cursor */
+        if (c == 0) continue;
+        Group g;
+        g.i1 = key / ns;
+        g.i2 = key % ns;
+        g.first = off;
+        g.count = c;
+        g.supported = class_pair_supported(T->cls[g.i1], T->cls[g.i2]);
+        P->groups.push_back(g);
+        off += c;
+    }
+    P->n_launches = (int32_t)P->groups.size();
+    plan_export_counts<<<(nk + 255) / 256 > 64 ? 64 : (nk + 255) / 256, 256, 0, stream>>>(P->d_mapped, P->d_counts, nk);
+    DCOL_CUDA(cudaGetLastError());
+    const unsigned blocks = (unsigned)((B + kPlanTile - 1) / kPlanTile);
     plan_scatter<<<blocks, kPlanThreads, 0, stream>>>(d_idx1, d_idx2, B, ns, nk, P->d_counts, P->d_perm);
     DCOL_CUDA(cudaGetLastError());
     return 0;
@@ -810,23 +891,32 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
 }
 
 /* streams, events and the two sets of device scratch (chunk pairs each) of the host entry points */
-static int host_pipeline_setup(dcol_shape_table* T, int64_t chunk)
+static int host_pipeline_setup(dcol_shape_table* T, int64_t chunk, int n_slots = 2)
 {
+    /* The counting sort of chunk i+1 runs while the pair kernels of chunk i fill every CTA slot, and the host thread
+     * waits for its histogram before it can launch anything else: on an equal-priority stream the sort's CTAs are only
+     * scheduled when the solve's grid drains, which serialises the host's per-chunk launch work with the solve.  The
+     * plan stream therefore gets the highest priority (its few CTAs take the next slots that free up). */
+    int prio_least = 0, prio_greatest = 0;
+    DCOL_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    if (getenv("DCOL_HOST_NOPRIO")) prio_greatest = prio_least; /* A/B switch of tools/diag_e2e.py */
     for (int i = 0; i < 4; ++i)
-        if (!T->streams[i]) DCOL_CUDA(cudaStreamCreateWithFlags(&T->streams[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+        if (!T->streams[i])
+            DCOL_CUDA(cudaStreamCreateWithPriority(&T->streams[i], cudaStreamNonBlocking, i == 1 ? prio_greatest : prio_least));
+    for (int i = 0; i < n_slots; ++i) {
+        if (!T->run[i]) DCOL_CUDA(cudaStreamCreateWithPriority(&T->run[i], cudaStreamNonBlocking, prio_least));
         if (!T->ev_in[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_in[i], cudaEventDisableTiming));
         if (!T->ev_plan[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_plan[i], cudaEventDisableTiming));
         if (!T->ev_done[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_done[i], cudaEventDisableTiming));
         if (!T->ev_out[i]) DCOL_CUDA(cudaEventCreateWithFlags(&T->ev_out[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < n_slots; ++i) {
         HostScratch& S = T->scratch[i];
         if (S.cap >= chunk) continue;
         S.release();
         dcol_plan_destroy(T->plans[i]);
         T->plans[i] = nullptr;
-        T->scene_key[i].clear();
+        if (i < 2) T->scene_key[i].clear();
         cudaError_t e = cudaMalloc(&S.idx1, sizeof(int32_t) * chunk);
         if (e == cudaSuccess) e = cudaMalloc(&S.idx2, sizeof(int32_t) * chunk);
         if (e == cudaSuccess) e = cudaMalloc(&S.iters, sizeof(int32_t) * chunk);
@@ -868,45 +958,76 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
     std::lock_guard<std::mutex> lock(T->mu);
     DCOL_DEVICE(T->device);
     const int64_t gw = (flags & DCOL_WANT_GRAD1) ? 6 : 12; /* doubles of gradient per pair */
-    int64_t kChunk = 1 << 20; /* measured on B200 + PCIe 5 (chunks of 2^18..2^22): 2^20 pairs gives the best overlap */
+    /* Chunk size, measured on B200 + PCIe 5 (tools/diag_e2e.py, tools/diag_host_trace.py; profiles/r02_host_pipeline.md):
+     * the call takes about copy-in + solve of ONE chunk plus the copy-out of everything (the slower direction), so smaller
+     * chunks would be better — but a chunk's solve is 40 small grids on 8 streams whose tails leave the SMs half empty
+     * (2^18 pairs: 1.0 ms instead of 0.37 ms), and below 2^20 pairs the solve, not PCIe, sets the period */
+    int64_t kChunk = 1 << 20;
+    int n_slots = dcol_shape_table::kSlots;
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
+    if (const char* env = getenv("DCOL_HOST_SLOTS")) n_slots = std::max(2, std::min(atoi(env), (int)dcol_shape_table::kSlots));
     const int64_t chunk = std::min<int64_t>(B, kChunk);
-    if (int rc0 = host_pipeline_setup(T, chunk)) return rc0;
-    T->scene_key[0].clear(); /* this call rebuilds both cached plans */
+    if (int rc0 = host_pipeline_setup(T, chunk, n_slots)) return rc0;
+    T->scene_key[0].clear(); /* this call rebuilds the cached plans */
     T->scene_key[1].clear();
     /* Four streams: copy-in, plan (counting sort), solve, copy-out.  The only host wait per chunk is for
      * that chunk's own histogram, so chunk i+1 is copied in and planned while chunk i is being solved and
      * chunk i-1 is being copied out. */
-    cudaStream_t s_in = T->streams[0], s_plan = T->streams[1], s_run = T->streams[2], s_out = T->streams[3];
+    cudaStream_t s_in = T->streams[0], s_plan = T->streams[1], s_out = T->streams[3];
+    const bool one_run_stream = getenv("DCOL_HOST_ONE_RUN_STREAM") != nullptr; /* A/B switch of tools/diag_e2e.py */
     int rc = 0;
     const int64_t n_chunks = (B + chunk - 1) / chunk;
+    /* DCOL_HOST_TRACE=1: device timeline of every chunk's stages and the host's enqueue times on stderr (diagnostic) */
+    const bool trace = getenv("DCOL_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> thost;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    const double host0 = now_ms();
+    if (trace) mark(s_in);
     for (int64_t ci = 0; ci < n_chunks && rc == 0; ++ci) {
-        const int slot = (int)(ci & 1);
+        const int slot = (int)(ci % n_slots);
         HostScratch& S = T->scratch[slot];
         dcol_plan* P = T->plans[slot];
+        cudaStream_t s_run = one_run_stream ? T->streams[2] : T->run[slot];
         const int64_t k0 = ci * chunk, n = std::min(chunk, B - k0);
-        if (ci >= 2) {
+        if (ci >= n_slots) {
+            DCOL_CUDA_BREAK(cudaEventSynchronize(T->ev_plan[slot])); /* the slot's scatter has read its cursors (long ago) */
             DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_in, T->ev_done[slot], 0));  /* inputs + perm consumed by the solve   */
             DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_plan, T->ev_done[slot], 0));
             DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_out[slot], 0));  /* previous outputs have left the device */
         }
+        if (trace) thost.push_back(now_ms() - host0);
+        mark(s_in);
         DCOL_CUDA_BREAK(cudaMemcpyAsync(S.idx1, idx1 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
         DCOL_CUDA_BREAK(cudaMemcpyAsync(S.idx2, idx2 + k0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_in));
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_in[slot], s_in));
         DCOL_CUDA_BREAK(cudaMemcpyAsync(S.pose1, pose1 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
         DCOL_CUDA_BREAK(cudaMemcpyAsync(S.pose2, pose2 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
+        mark(s_in);
         DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_plan, T->ev_in[slot], 0));
-        rc = plan_build(P, S.idx1, S.idx2, n, s_plan);
+        rc = plan_build_host_counts(P, idx1 + k0, idx2 + k0, S.idx1, S.idx2, n, s_plan);
         if (rc) break;
+        if (trace) thost.push_back(now_ms() - host0);
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_plan[slot], s_plan));
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_in[slot], s_in)); /* now also covers the poses */
         DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_plan[slot], 0));
         DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_run, T->ev_in[slot], 0));
+        mark(s_run);
         rc = dcol_proximity_batch_device(P, S.pose1, S.pose2, tol, max_iter, flags, S.alpha, S.contact, S.grad, S.iters,
                                          S.status, s_run);
         if (rc) break;
+        mark(s_run);
+        if (trace) thost.push_back(now_ms() - host0);
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_done[slot], s_run));
         DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_out, T->ev_done[slot], 0));
+        mark(s_out);
         DCOL_CUDA_BREAK(cudaMemcpyAsync(alpha + k0, S.alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s_out));
         DCOL_CUDA_BREAK(cudaMemcpyAsync(iters + k0, S.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
         DCOL_CUDA_BREAK(cudaMemcpyAsync(status + k0, S.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_out));
@@ -915,11 +1036,25 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         if (flags & DCOL_WANT_GRAD)
             DCOL_CUDA_BREAK(cudaMemcpyAsync(grad + gw * k0, S.grad, sizeof(double) * gw * n, cudaMemcpyDeviceToHost, s_out));
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_out[slot], s_out));
+        mark(s_out);
     }
     cudaError_t e = cudaStreamSynchronize(s_out);
     cudaStreamSynchronize(s_in);
     cudaStreamSynchronize(s_plan);
-    cudaStreamSynchronize(s_run);
+    cudaStreamSynchronize(T->streams[2]);
+    for (int i = 0; i < n_slots; ++i) cudaStreamSynchronize(T->run[i]);
+    if (trace) {
+        /* events per chunk: in0 in1(pose copies enqueued) run0 run1 out0 out1, after the call's first mark */
+        fprintf(stderr, "chunk  host:enq sync launched | dev: in0 in1 run0 run1 out0 out1 (ms since the first copy was enqueued)\n");
+        for (size_t c = 0; 1 + 6 * (c + 1) <= tev.size() && 3 * (c + 1) <= thost.size(); ++c) {
+            float v[6];
+            for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&v[j], tev[0], tev[1 + 6 * c + j]);
+            fprintf(stderr, "%5zu  %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f\n", c, thost[3 * c], thost[3 * c + 1],
+                    thost[3 * c + 2], v[0], v[1], v[2], v[3], v[4], v[5]);
+        }
+        fprintf(stderr, "host total %.3f ms\n", now_ms() - host0);
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+    }
     if (rc == 0 && e != cudaSuccess) rc = fail_cuda(e, "dcol_proximity_batch_host");
     return rc;
 }

@@ -24,17 +24,26 @@ eng = d.ProximityEngine(shapes)
 hi1, hi2 = d.pinned_empty(B, np.int32), d.pinned_empty(B, np.int32)
 hp1, hp2 = d.pinned_empty((B, 6)), d.pinned_empty((B, 6))
 hi1[:], hi2[:], hp1[:], hp2[:] = i1, i2, p1, p2
-out = d.BatchResult(alpha=d.pinned_empty(B), contact=d.pinned_empty((B, 3)), grad=d.pinned_empty((B, 12)),
-                    iters=d.pinned_empty(B, np.int32), status=d.pinned_empty(B, np.int32))
-for chunk in (1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 23):
-    os.environ["DCOL_HOST_CHUNK"] = str(chunk)
-    for nb in (B,):
-        eng.solve_host(hi1[:nb], hi2[:nb], hp1[:nb], hp2[:nb], out=d.BatchResult(out.alpha[:nb], out.contact[:nb], out.grad[:nb], out.iters[:nb], out.status[:nb]))
-        t = time.perf_counter()
-        for _ in range(3):
-            eng.solve_host(hi1[:nb], hi2[:nb], hp1[:nb], hp2[:nb], out=d.BatchResult(out.alpha[:nb], out.contact[:nb], out.grad[:nb], out.iters[:nb], out.status[:nb]))
-        dt = (time.perf_counter() - t) / 3
-        print(f"chunk {chunk} pairs {nb}: {dt*1e3:.1f} ms  {nb/dt/1e6:.1f} Mpairs/s  {(nb*240)/dt/1e9:.1f} GB/s both ways", flush=True)
+out = d.BatchResult(alpha=d.pinned_empty(B), contact=None, grad=d.pinned_empty((B, 12)),
+                    iters=d.pinned_empty(B, np.int32), status=d.pinned_empty(B, np.int32))   # what bench.py's e2e leg moves
+for noprio in ((True, False) if '--prio-ab' in sys.argv else (False,)):
+    if noprio:
+        os.environ["DCOL_HOST_NOPRIO"] = "1"
+    else:
+        os.environ.pop("DCOL_HOST_NOPRIO", None)
+    eng = d.ProximityEngine(shapes)   # the host pipeline's streams are created per table
+    for slots in ((2, 4) if '--slots-ab' in sys.argv else (4,)):
+        os.environ["DCOL_HOST_SLOTS"] = str(slots)
+        for chunk in (1 << 17, 1 << 18, 1 << 19, 1 << 20):
+            os.environ["DCOL_HOST_CHUNK"] = str(chunk)
+            eng.solve_host(hi1, hi2, hp1, hp2, out=out)
+            eng.solve_host(hi1, hi2, hp1, hp2, out=out)
+            t = time.perf_counter()
+            for _ in range(5):
+                eng.solve_host(hi1, hi2, hp1, hp2, out=out)
+            dt = (time.perf_counter() - t) / 5
+            print(f"side streams {os.environ.get('DCOL_SIDE_STREAMS', 'default')} plan-stream priority {not noprio} slots {slots} chunk {chunk} pairs {B}: {dt*1e3:.2f} ms  {B/dt/1e6:.1f} Mpairs/s  {(B*216)/dt/1e9:.1f} GB/s both ways", flush=True)
+del os.environ["DCOL_HOST_SLOTS"], os.environ["DCOL_HOST_CHUNK"]
 # pageable
 t = time.perf_counter(); r = eng.solve_host(i1, i2, p1, p2); dt = time.perf_counter() - t
 print(f"pageable numpy buffers: {dt*1e3:.1f} ms", flush=True)
