@@ -480,10 +480,10 @@ struct Block {
     /* iterate */
     double so[P::NOA], zo[P::NOA]; /* orthant slack / dual                                   */
     double sq[P::QA], zq[P::QA];   /* second-order-cone slack / dual (body-frame components) */
-    /* orthant temporaries */
-    double rinv[P::NOA]; /* 1 / lambda_i = 1 / sqrt(s_i z_i)                                */
-    double ta[P::NOA];   /* rho~_i = (W^-1 rz)_i, later ds~_i                               */
-    double tb[P::NOA];   /* k_i, later dz~_i                                                */
+    /* orthant temporaries (relative steps: see pass_a) */
+    double rinv[P::NOA]; /* 1 / (s_i z_i) = 1 / lambda_i^2                                  */
+    double ta[P::NOA];   /* rz_i = s_i + (G x - h)_i, later ds_i / s_i                      */
+    double tb[P::NOA];   /* (ds_i / s_i)(dz_i / z_i) of the affine step, later dz_i / z_i   */
     /* soc temporaries */
     double lam[P::QA], tq[P::QA], kq[P::QA];
     double wh[P::QA]; /* J wbar = (wbar_0, -wbar_v): W^-1 = (1/eta) Wbar(wh), W = eta Wbar(J wh) */
@@ -713,7 +713,7 @@ struct Solver {
             if (P::dyn && i >= no) break;
             const double pr = B.so[i] * B.zo[i];
             sz += pr;
-            B.rinv[i] = rsqrt_(pr); /* NT_scaling.py:430: W_ort = sqrt(s/z); lambda = W z = sqrt(s z) */
+            B.rinv[i] = rcp_(pr); /* NT_scaling.py:430: W_ort = sqrt(s/z), lambda = W z = sqrt(s z); only lambda^-2 is used */
         }
         if (P::Q > 0) {
             /* NT_scaling.py:340-405 */
@@ -760,13 +760,16 @@ struct Solver {
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
-            const double ri = B.rinv[i];
-            const double winv = B.zo[i] * ri;                             /* 1 / w_i                       */
+            /* On the orthant the scaled directions are never formed: with the relative steps ds_i / s_i = ds~_i / lambda_i
+             * and dz_i / z_i = dz~_i / lambda_i every product with w_i or lambda_i collapses into 1 / s_i = z_i / (s_i z_i)
+             * and w_i^-2 = z_i / s_i, both line searches read the relative steps directly, and no square root is needed
+             * (same Newton system and step lengths as NT_scaling.py:430 / pdip.py:7-22, 424-466 in exact arithmetic) */
+            const double is = B.zo[i] * B.rinv[i];                        /* 1 / s_i                       */
             const double rz = P::row_dot(c, i, xh, B.so[i]);              /* rz_i = s_i + (G x - h)_i      */
-            B.ta[i] = winv * rz;                                          /* rho~_i = (W^-1 rz)_i          */
+            B.ta[i] = rz;
             /* Gram += w^-2 g g^T and acc_a -= w^-2 rz g  (b~_affine = lambda - rho~; G~^T lambda = G^T z cancels in bx) */
-            P::row_gram_axpy(c, i, winv * winv, rz, Gl, acc_a);
-            P::row_axpy(c, i, winv * ri, acc_l);                          /* W^-1 (lambda^-1 o e) */
+            P::row_gram_axpy(c, i, B.zo[i] * is, rz, Gl, acc_a);
+            P::row_axpy(c, i, is, acc_l);                                 /* W^-1 (lambda^-1 o e) = g / s_i */
         }
         if (P::Q > 0) {
             /* lambda = W z */
@@ -848,18 +851,17 @@ struct Solver {
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
-            const double ri = B.rinv[i];
-            const double winv = B.zo[i] * ri;
-            const double lam = B.so[i] * winv; /* lambda_i = s_i / w_i */
-            /* ds~ = W^-1 ds with ds = -rz - G dx (primal equation), dz~ = d - ds~ with d = -lambda (complementarity) */
-            const double ds = -fma(winv, P::row_dot(c, i, xh), B.ta[i]);
-            const double dz = -lam - ds;
-            /* both searches run against lambda_i > 0: max(-ds/l, -dz/l) = -min(ds, dz)/l */
-            tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
-            d_sz += ds * dz;
-            const double k = (ds * dz) * ri;
-            B.tb[i] = k;
-            P::row_axpy(c, i, winv * k, acc_k);
+            const double is = B.zo[i] * B.rinv[i];
+            /* ds = -rz - G dx (primal equation) and s dz + z ds = -s z (complementarity), as relative steps */
+            const double ds = -(is * P::row_dot(c, i, xh, B.ta[i])); /* ds_i / s_i */
+            const double dz = -1.0 - ds;                              /* dz_i / z_i */
+            /* both searches: max(-ds/s, -dz/z) */
+            tm[i & 1] = max_(tm[i & 1], -min_(ds, dz));
+            const double t = ds * dz;        /* ds~ dz~ / lambda^2 */
+            const double zt = B.zo[i] * t;
+            d_sz = fma(B.so[i], zt, d_sz);   /* <ds~, dz~> = sum s z t */
+            B.tb[i] = t;
+            P::row_axpy(c, i, zt, acc_k);    /* W^-1 (lambda^-1 o (ds~ o dz~)) = g z t */
         }
         if (P::Q > 0) {
             double g[P::QA], dz[P::QA], ds[P::QA], w[P::QA];
@@ -904,13 +906,12 @@ struct Solver {
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
-            const double ri = B.rinv[i];
-            const double winv = B.zo[i] * ri;
-            const double lam = B.so[i] * winv; /* lambda_i = s_i / w_i */
-            const double d = -lam - B.tb[i] + sigmu * ri; /* lambda^-1 o ds */
-            const double ds = -fma(winv, P::row_dot(c, i, xh), B.ta[i]); /* -rho~ - G~ dx (primal equation) */
-            const double dz = d - ds;
-            tm[i & 1] = max_(tm[i & 1], -min_(ds, dz) * ri);
+            const double ip = B.rinv[i];
+            const double is = B.zo[i] * ip;
+            const double d = fma(sigmu, ip, -1.0 - B.tb[i]);          /* (lambda^-1 o ds) / lambda = -1 - t + sigma mu / (s z) */
+            const double ds = -(is * P::row_dot(c, i, xh, B.ta[i])); /* ds_i / s_i (primal equation) */
+            const double dz = d - ds;                                 /* dz_i / z_i */
+            tm[i & 1] = max_(tm[i & 1], -min_(ds, dz));
             B.ta[i] = ds;
             B.tb[i] = dz;
         }
@@ -943,9 +944,8 @@ struct Solver {
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
-            const double ar = a * B.rinv[i]; /* a w_i = s_i (a / lambda_i),  a / w_i = z_i (a / lambda_i) */
-            B.so[i] = fma(B.so[i] * ar, B.ta[i], B.so[i]);
-            B.zo[i] = fma(B.zo[i] * ar, B.tb[i], B.zo[i]);
+            B.so[i] = fma(a * B.ta[i], B.so[i], B.so[i]); /* s (1 + a ds/s) */
+            B.zo[i] = fma(a * B.tb[i], B.zo[i], B.zo[i]);
         }
         if (P::Q > 0) {
             double ds[P::QA], dz[P::QA];
@@ -1278,8 +1278,7 @@ struct Solver {
         DCOL_UNROLL_ROWS
         for (int i = 0; i < P::NO; ++i) {
             if (P::dyn && i >= no) break;
-            const double winv = B.zo[i] * B.rinv[i];
-            vo[i] *= winv * winv; /* w_i^-2 = z_i / s_i */
+            vo[i] *= B.zo[i] * (B.zo[i] * B.rinv[i]); /* w_i^-2 = z_i / s_i = z_i^2 / (s_i z_i) */
         }
         if (P::Q > 0) {
             /* W^-2 = (2 wh wh^T - J) / eta^2, as in pass_a */
