@@ -86,6 +86,17 @@ DCOL_HD double rcp_(double x)
     return 1.0 / x;
 #endif
 }
+/* sqrt(x) for the cone norms of the line searches: x * rsqrt_(x), one rounding worse than the library's correctly
+ * rounded routine at a third of its instructions; 0 -> 0, negative or NaN -> NaN */
+DCOL_HD double sqrt_(double x)
+{
+#if defined(__CUDA_ARCH__)
+    const double r = x * rsqrt_(x);
+    return (x == 0.0) ? 0.0 : r;
+#else
+    return sqrt(x);
+#endif
+}
 DCOL_HD double max_(double a, double b) { return (b > a) ? b : a; } /* Python max(a, b): keeps a on NaN */
 DCOL_HD double min_(double a, double b) { return (b < a) ? b : a; }
 /* 0 if x is finite, NaN otherwise (x * 0 is NaN for inf and NaN) */
@@ -734,9 +745,12 @@ struct Solver {
             const double e2 = (Js * rs) * rz; /* sqrt(Js / Jz) */
             B.ieta = rsqrt_(e2);
             B.eta = e2 * B.ieta;
-            bad += nonfinite_probe(B.eta) + nonfinite_probe(B.ieta) + nonfinite_probe(B.bw);
+            /* one probe for the whole scaling: a sum is non-finite exactly when one of its terms is (a non-finite
+             * ieta makes eta = e2 ieta non-finite as well) */
+            double pr = B.eta + B.bw;
             DCOL_UNROLL
-            for (int i = 0; i < P::Q; ++i) bad += nonfinite_probe(B.wh[i]);
+            for (int i = 0; i < P::Q; ++i) pr += B.wh[i];
+            bad += nonfinite_probe(pr);
         }
         return sz;
     }
@@ -833,7 +847,35 @@ struct Solver {
             const double rv = d[i] * B.ls_isn - coef * (B.lam[i] * B.ls_inu);
             nn += rv * rv;
         }
-        return sqrt(nn) - rho0;
+        return sqrt_(nn) - rho0;
+    }
+    /* The two searches of the AFFINE step at once.  There ds~ + dz~ = -lambda, and with nu = J(lambda)
+     * the vector part of rho(ds~) is minus that of rho(dz~): zeta_s = -nu - zeta_z, coef_s = -sqrt(nu) - coef_z, so
+     * ds~_i / sqrt(nu) - coef_s lambda_i / nu = -(dz~_i / sqrt(nu) - coef_z lambda_i / nu).  One norm serves both; only
+     * rho_0 differs.  Same values as two calls of soc_ls up to rounding — except below the 1e-25 floor that
+     * pdip.py:39-47 puts under J(lambda), where nu is no longer J(lambda): that needs an iterate within 1e-25 of the
+     * cone's boundary, i.e. one that has already broken down (J(lambda) = sqrt(J(s) J(z)) stays of the order of mu, and
+     * the solver stops at mu < tol), and the failure statuses are decided elsewhere (finiteness of the scaling, pivots). */
+    template <class P>
+    DCOL_HD static void soc_ls_affine(const Block<P>& B, const double (&ds)[P::QA], const double (&dz)[P::QA], double& ms,
+                                      double& mz)
+    {
+        double zeta_z = B.lam[0] * dz[0], zeta_s = B.lam[0] * ds[0];
+        DCOL_UNROLL
+        for (int i = 1; i < P::Q; ++i) {
+            zeta_z -= B.lam[i] * dz[i];
+            zeta_s -= B.lam[i] * ds[i];
+        }
+        const double coef = (zeta_z * B.ls_isn + dz[0]) * B.ls_c0;
+        double nn = 0.0;
+        DCOL_UNROLL
+        for (int i = 1; i < P::Q; ++i) {
+            const double rv = dz[i] * B.ls_isn - coef * (B.lam[i] * B.ls_inu);
+            nn += rv * rv;
+        }
+        const double r = sqrt_(nn);
+        mz = r - zeta_z * B.ls_inu;
+        ms = r - zeta_s * B.ls_inu;
     }
 
     /* ---- pass B: affine direction of one block, its line-search measures, the three dot products of
@@ -872,8 +914,12 @@ struct Solver {
                 ds[i] = -B.lam[i] - dz[i];
                 d_sz += ds[i] * dz[i];
             }
-            tm[0] = max_(tm[0], soc_ls<P>(B, ds));
-            tm[1] = max_(tm[1], soc_ls<P>(B, dz));
+            {
+                double ms, mz;
+                soc_ls_affine<P>(B, ds, dz, ms, mz);
+                tm[0] = max_(tm[0], ms);
+                tm[1] = max_(tm[1], mz);
+            }
             /* w = ds~ o dz~ (pdip.py:165-200); k = lambda^-1 o w (pdip.py:88-122) */
             w[0] = 0.0;
             DCOL_UNROLL
