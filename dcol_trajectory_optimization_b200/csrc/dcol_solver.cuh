@@ -496,7 +496,9 @@ struct Block {
     double ta[P::NOA];   /* rz_i = s_i + (G x - h)_i, later ds_i / s_i                      */
     double tb[P::NOA];   /* (ds_i / s_i)(dz_i / z_i) of the affine step, later dz_i / z_i   */
     /* soc temporaries */
-    double lam[P::QA], tq[P::QA], kq[P::QA];
+    double lam[P::QA]; /* lambda = W z                                                      */
+    double tq[P::QA];  /* rz = s + (G x - h), later the corrector's ds (both unscaled)       */
+    double kq[P::QA];  /* k = lambda^-1 o (ds~ o dz~), later the corrector's dz~            */
     double wh[P::QA]; /* J wbar = (wbar_0, -wbar_v): W^-1 = (1/eta) Wbar(wh), W = eta Wbar(J wh) */
     double eta, ieta, bw;
     double ls_isn, ls_inu, ls_c0; /* shared line-search terms of lambda, pdip.py:39-47      */
@@ -646,6 +648,54 @@ struct Solver {
             v[i] = t * Li[i];
         }
     }
+    /* ---- the Newton systems use the square-root-free factor M = L D L^T of the same matrix (unit lower L; Di = 1 / d_j;
+     * the strict upper triangle of L holds U_ik = L_ik d_k while factoring).  The pivots d_j are the squares of the
+     * Cholesky pivots, so the `<= 0` / NaN tests decide exactly as above; what it buys is latency: a reciprocal instead
+     * of a reciprocal square root per column, and substitutions that are pure multiply-add chains (the divisions by the
+     * diagonal become one independent scaling between the two sweeps) — these chains are the serial part of an
+     * iteration, which two warps per scheduler cannot hide.  The initial point keeps chol(): it needs the factor's
+     * diagonal itself (pdip.py:326). */
+    DCOL_HD static int ldlt(const double (&M)[N][N], double (&L)[N][N], double (&Di)[N])
+    {
+        int status = 0;
+        DCOL_UNROLL
+        for (int j = 0; j < N; ++j) {
+            double d = M[j][j];
+            DCOL_UNROLL
+            for (int k = 0; k < j; ++k) d -= L[j][k] * L[k][j];
+            if (status == 0 && !(d > 0.0)) status = (d != d) ? DCOL_STATUS_NON_FINITE : DCOL_STATUS_NOT_PD;
+            const double rd = rcp_(d);
+            Di[j] = rd;
+            DCOL_UNROLL
+            for (int i = j + 1; i < N; ++i) {
+                double v = M[j][i];
+                DCOL_UNROLL
+                for (int k = 0; k < j; ++k) v -= L[i][k] * L[k][j];
+                L[j][i] = v;      /* U_ij = L_ij d_j */
+                L[i][j] = v * rd;
+            }
+        }
+        return status;
+    }
+    DCOL_HD static void ldlt_solve(const double (&L)[N][N], const double (&Di)[N], double (&v)[N])
+    {
+        DCOL_UNROLL
+        for (int i = 1; i < N; ++i) {
+            double t = v[i];
+            DCOL_UNROLL
+            for (int k = 0; k < i; ++k) t -= L[i][k] * v[k];
+            v[i] = t;
+        }
+        DCOL_UNROLL
+        for (int i = 0; i < N; ++i) v[i] *= Di[i];
+        DCOL_UNROLL
+        for (int i = N - 2; i >= 0; --i) {
+            double t = v[i];
+            DCOL_UNROLL
+            for (int k = i + 1; k < N; ++k) t -= L[k][i] * v[k];
+            v[i] = t;
+        }
+    }
     DCOL_HD static double probe_vec(const double (&v)[N])
     {
         double t = 0.0;
@@ -788,10 +838,12 @@ struct Solver {
         if (P::Q > 0) {
             /* lambda = W z */
             wbar_apply<P::Q>(B.wh, B.bw, -1.0, B.zq, B.eta, B.lam);
-            double rzq[P::QA];
+            /* rz = s + (G x - h) is kept UNSCALED (in tq): the Newton steps need W^-1 (G dx + rz) = G~ dx + rho~ and the
+             * update of s needs ds = -(G dx + rz) itself (primal equation), so rho~ = W^-1 rz is only a temporary here */
+            double rho[P::QA];
             DCOL_UNROLL
-            for (int i = 0; i < P::Q; ++i) rzq[i] = B.sq[i] + rq[i];
-            wbar_apply<P::Q>(B.wh, B.bw, 1.0, rzq, B.ieta, B.tq); /* rho~ = W^-1 rz */
+            for (int i = 0; i < P::Q; ++i) B.tq[i] = B.sq[i] + rq[i];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.tq, B.ieta, rho); /* rho~ = W^-1 rz */
             /* W^-2 for the Gram block.  Wbar(w)^2 = 2 w w^T - J for w^T J w = 1, so
              * W^-2 = (2 wh wh^T - J) / eta^2: ten products instead of forming W^-1 and squaring it. */
             double W2[P::QA][P::QA];
@@ -818,7 +870,7 @@ struct Solver {
             double t1[P::QA], t2[P::QA];
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
-                t1[i] = -B.tq[i];
+                t1[i] = -rho[i];
                 t2[i] = (i == 0 ? B.lam[i] : -B.lam[i]) * B.irho;
             }
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, t1, B.ieta, qa);
@@ -906,12 +958,14 @@ struct Solver {
             P::row_axpy(c, i, zt, acc_k);    /* W^-1 (lambda^-1 o (ds~ o dz~)) = g z t */
         }
         if (P::Q > 0) {
-            double g[P::QA], dz[P::QA], ds[P::QA], w[P::QA];
-            wbar_apply<P::Q>(B.wh, B.bw, 1.0, rq, B.ieta, g); /* G~ dx */
+            double g[P::QA], dz[P::QA], ds[P::QA], w[P::QA], v[P::QA];
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) v[i] = rq[i] + B.tq[i];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, v, B.ieta, g); /* G~ dx + rho~ = -ds~ (primal equation) */
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
-                dz[i] = g[i] - (B.lam[i] - B.tq[i]);
-                ds[i] = -B.lam[i] - dz[i];
+                ds[i] = -g[i];
+                dz[i] = g[i] - B.lam[i]; /* ds~ + dz~ = -lambda (complementarity) */
                 d_sz += ds[i] * dz[i];
             }
             {
@@ -939,8 +993,8 @@ struct Solver {
         p.template from_local_add<N>(acc_k, col_e, vk);
     }
 
-    /* ---- pass C: corrector direction of one block (stored as ds~ in ta/tq, dz~ in tb/kq) and its
-     * line-search measures */
+    /* ---- pass C: corrector direction of one block (orthant: relative steps in ta / tb; cone: unscaled ds in tq, dz~ in
+     * kq) and its line-search measures */
     template <class P>
     DCOL_HD static void pass_c(const P& p, const typename P::Const& c, int col_e, Block<P>& B, const double (&dx)[N],
                                double sigmu, double (&tm)[2])
@@ -962,21 +1016,22 @@ struct Solver {
             B.tb[i] = dz;
         }
         if (P::Q > 0) {
-            double g[P::QA], dz[P::QA], ds[P::QA];
-            wbar_apply<P::Q>(B.wh, B.bw, 1.0, rq, B.ieta, g);
+            double g[P::QA], dz[P::QA], ds[P::QA], v[P::QA];
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) v[i] = rq[i] + B.tq[i];
+            wbar_apply<P::Q>(B.wh, B.bw, 1.0, v, B.ieta, g); /* -ds~ (primal equation) */
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
                 const double li = (i == 0 ? B.lam[i] : -B.lam[i]) * B.irho; /* lambda^-1 o e */
-                const double d = -B.lam[i] - B.kq[i] + sigmu * li;
-                const double bt = -B.tq[i] - d;
-                dz[i] = g[i] - bt;
-                ds[i] = d - dz[i];
+                const double d = -B.lam[i] - B.kq[i] + sigmu * li;          /* ds~ + dz~ */
+                ds[i] = -g[i];
+                dz[i] = d + g[i];
             }
             tm[0] = max_(tm[0], soc_ls<P>(B, ds));
             tm[1] = max_(tm[1], soc_ls<P>(B, dz));
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
-                B.tq[i] = ds[i];
+                B.tq[i] = -v[i]; /* ds = W ds~, unscaled: -(G dx + rz) */
                 B.kq[i] = dz[i];
             }
         }
@@ -994,12 +1049,11 @@ struct Solver {
             B.zo[i] = fma(a * B.tb[i], B.zo[i], B.zo[i]);
         }
         if (P::Q > 0) {
-            double ds[P::QA], dz[P::QA];
-            wbar_apply<P::Q>(B.wh, B.bw, -1.0, B.tq, B.eta, ds);
+            double dz[P::QA];
             wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.kq, B.ieta, dz);
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) {
-                B.sq[i] += a * ds[i];
+                B.sq[i] += a * B.tq[i]; /* pass_c left the unscaled ds here */
                 B.zq[i] += a * dz[i];
             }
         }
@@ -1154,8 +1208,8 @@ struct Solver {
         double dx[N];
         DCOL_UNROLL
         for (int j = 0; j < N; ++j) dx[j] = va[j]; /* bx + G~^T b~ */
-        if (int bad = chol(M, L, Li)) return bad; /* scipy cholesky: check_finite, LinAlgError */
-        chol_solve(L, Li, dx);
+        if (int bad = ldlt(M, L, Li)) return bad; /* scipy cholesky: check_finite, LinAlgError */
+        ldlt_solve(L, Li, dx);
 
         /* affine step: un-damped line search, sigma = clip(rho, 0, 1)^3   pdip.py:446-448 */
         double tm[2] = { 0.0, 0.0 }, d_sz = 0.0, vk[N];
@@ -1173,7 +1227,7 @@ struct Solver {
         /* corrector: rhs = rhs_affine + G~^T k - sigma mu G~^T (lambda^-1 o e), same factor   pdip.py:450-460 */
         DCOL_UNROLL
         for (int j = 0; j < N; ++j) dx[j] = va[j] + vk[j] - sigmu * vl[j];
-        chol_solve(L, Li, dx);
+        ldlt_solve(L, Li, dx);
         tm[0] = 0.0;
         tm[1] = 0.0;
         pass_c<F1>(p1, c1, CE1, b1, dx, sigmu, tm);
