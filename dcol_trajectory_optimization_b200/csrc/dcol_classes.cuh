@@ -94,7 +94,13 @@ inline void fill_const(const dcol_shape& s, const double* A, const double* b, Sh
         for (int j = 0; j < 3; ++j) c.Q_off[i][j] = s.Q_offset[3 * i + j];
     }
     c.nf = s.n_faces;
-    c.pad = 0;
+    c.no_offset = 1;
+    for (int i = 0; i < 3; ++i) {
+        if (s.r_offset[i] != 0.0) c.no_offset = 0;
+        for (int j = 0; j < 3; ++j)
+            if (s.Q_offset[3 * i + j] != (i == j ? 1.0 : 0.0)) c.no_offset = 0;
+    }
+    for (int i = 0; i < 21; ++i) c.G0[i] = 0.0;
     for (int i = 0; i < (FMAX > 0 ? FMAX : 1); ++i) {
         c.A[i][0] = c.A[i][1] = c.A[i][2] = 0.0;
         c.b[i] = 0.0;
@@ -103,6 +109,14 @@ inline void fill_const(const dcol_shape& s, const double* A, const double* b, Sh
         for (int j = 0; j < 3; ++j) c.A[i][j] = A[3 * (s.face_off + i) + j];
         c.b[i] = b[s.face_off + i];
     }
+}
+
+/* the constant block of primitive class P: the shape's fields plus the constants derived from them */
+template <class P>
+inline void fill_const_prim(const dcol_shape& s, const double* A, const double* b, typename P::Const& c)
+{
+    fill_const(s, A, b, c);
+    Solver<P, P>::template gram0<P>(c);
 }
 
 /* Runtime (c1, c2) -> compile-time pair of classes.  f must provide

@@ -612,8 +612,8 @@ cudaError_t launch_pair(const GroupLaunch& g, cudaStream_t stream)
     typedef typename ClassPrim<C1>::type P1;
     typedef typename ClassPrim<C2>::type P2;
     GroupArgs<P1, P2> a;
-    fill_const(*g.s1, g.A, g.b, a.c1);
-    fill_const(*g.s2, g.A, g.b, a.c2);
+    fill_const_prim<P1>(*g.s1, g.A, g.b, a.c1);
+    fill_const_prim<P2>(*g.s2, g.A, g.b, a.c2);
     a.b = g.args;
     if (g.args.count <= 0) return cudaSuccess;
     if constexpr (!JAC && !P1::dyn && !P2::dyn) {

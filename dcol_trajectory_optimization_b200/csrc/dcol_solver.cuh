@@ -159,7 +159,12 @@ struct ShapeConst {
     double ia[3];           /* ellipsoid: inverse semi-axes           */
     double r_off[3];        /* body-frame origin offset               */
     double Q_off[3][3];     /* body-frame rotation offset             */
-    int32_t nf, pad;        /* faces actually present                 */
+    int32_t nf;             /* faces actually present                 */
+    int32_t no_offset;      /* r_off = 0 and Q_off = I (every shape of the reference's scenes): the products with them are skipped */
+    /* G^T G of this shape's rows in its own local variables (upper triangle, row-major packed, NL <= 6): a constant of
+     * the shape, which is all the initial point's normal equations need (Solver::init_accumulate); filled on the host
+     * by fill_const_prim (dcol_classes.cuh) */
+    double G0[21];
     double A[FMAX > 0 ? FMAX : 1][3];
     double b[FMAX > 0 ? FMAX : 1];
 };
@@ -257,6 +262,15 @@ struct Prim {
     /* pose -> (Q', r')   problem_matrices.py:272-364 */
     DCOL_HD void set_pose(const Const& c, const double r[3], const double Qm[3][3])
     {
+        if (c.no_offset) { /* warp-uniform */
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                rp[i] = r[i];
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) Qp[i][j] = rot ? Qm[i][j] : (i == j ? 1.0 : 0.0);
+            }
+            return;
+        }
         DCOL_UNROLL
         for (int i = 0; i < 3; ++i) {
             rp[i] = r[i] + (Qm[i][0] * c.r_off[0] + Qm[i][1] * c.r_off[1] + Qm[i][2] * c.r_off[2]);
@@ -721,39 +735,57 @@ struct Solver {
         p.template from_local_add<N>(acc, col_e, out);
     }
 
-    /* ---- pdip.py:291-332, one primitive's share of M = G^T G and of G^T h */
+    /* ---- pdip.py:291-332, one primitive's share of M = G^T G and of G^T h.  In the primitive's local variables both
+     * come from ONE constant of the shape, G0 = sum_i g_i g_i^T (+ the cone rows): G^T G = T^T G0 T, and because the rows
+     * have no constant term in local variables, h_i = g_i[0:3] . u with u = Q'^T r' (minus the local coordinates of the
+     * world origin), so G^T h = T^T (G0[:, 0:3] u). */
     template <class P>
     DCOL_HD static void init_accumulate(const P& p, const typename P::Const& c, int col_e, double (&M)[N][N],
                                         double (&gth)[N])
     {
         double Gl[P::NL][P::NL];
-        DCOL_UNROLL
-        for (int i = 0; i < P::NL; ++i) {
+        {
+            int at = 0;
             DCOL_UNROLL
-            for (int j = 0; j < P::NL; ++j) Gl[i][j] = 0.0;
+            for (int i = 0; i < P::NL; ++i) {
+                DCOL_UNROLL
+                for (int j = i; j < P::NL; ++j) Gl[i][j] = c.G0[at++];
+            }
         }
+        p.template gram_from_local<N>(Gl, col_e, M);
+        if constexpr (!P::ident) {
+            double u[3], acc[P::NL];
+            DCOL_UNROLL
+            for (int j = 0; j < 3; ++j)
+                u[j] = P::frot ? (p.Qp[0][j] * p.rp[0] + p.Qp[1][j] * p.rp[1] + p.Qp[2][j] * p.rp[2]) : p.rp[j];
+            DCOL_UNROLL
+            for (int j = 0; j < P::NL; ++j) {
+                double t = 0.0;
+                DCOL_UNROLL
+                for (int k = 0; k < 3; ++k) t += (j <= k ? Gl[j][k] : Gl[k][j]) * u[k];
+                acc[j] = t;
+            }
+            p.template from_local_add<N>(acc, col_e, gth);
+        }
+    }
+    /* the shape constant G0 (host side, when the constant block of a launch is filled) */
+    template <class P>
+    static void gram0(typename P::Const& c)
+    {
+        double Gl[P::NL][P::NL];
+        for (int i = 0; i < P::NL; ++i)
+            for (int j = 0; j < P::NL; ++j) Gl[i][j] = 0.0;
         double ones[P::NOA];
-        DCOL_UNROLL
         for (int i = 0; i < P::NOA; ++i) ones[i] = 1.0;
         P::ort_gram(c, ones, Gl);
         double I2[P::QA][P::QA];
-        DCOL_UNROLL
-        for (int i = 0; i < P::QA; ++i) {
-            DCOL_UNROLL
+        for (int i = 0; i < P::QA; ++i)
             for (int j = 0; j < P::QA; ++j) I2[i][j] = (i == j) ? 1.0 : 0.0;
-        }
         P::soc_gram(c, I2, Gl);
-        p.template gram_from_local<N>(Gl, col_e, M);
-        /* h = -(G 0 - h): rows at the world origin, negated */
-        double zero[N], ro[P::NOA], rq[P::QA];
-        DCOL_UNROLL
-        for (int j = 0; j < N; ++j) zero[j] = 0.0;
-        rows<P, true>(p, c, col_e, zero, ro, rq);
-        DCOL_UNROLL
-        for (int i = 0; i < P::NOA; ++i) ro[i] = -ro[i];
-        DCOL_UNROLL
-        for (int i = 0; i < P::QA; ++i) rq[i] = -rq[i];
-        rows_t<P>(p, c, col_e, ro, rq, gth);
+        int at = 0;
+        for (int i = 0; i < 21; ++i) c.G0[i] = 0.0;
+        for (int i = 0; i < P::NL; ++i)
+            for (int j = i; j < P::NL; ++j) c.G0[at++] = Gl[i][j];
     }
 
     /* ---- NT scaling of one block + everything of pass A that does not need the Newton step.
@@ -1085,16 +1117,24 @@ struct Solver {
         DCOL_UNROLL
         for (int i = 0; i < 3; ++i)
             gr[i] = zw[i] - (P::rot ? (pw.Qp[i][0] * acc[0] + pw.Qp[i][1] * acc[1] + pw.Qp[i][2] * acc[2]) : acc[i]);
-        double qu[3], qe[3];
-        DCOL_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            qu[i] = c.Q_off[i][0] * acc[0] + c.Q_off[i][1] * acc[1] + c.Q_off[i][2] * acc[2];
-            qe[i] = c.Q_off[i][0] * eh[0] + c.Q_off[i][1] * eh[1] + c.Q_off[i][2] * eh[2];
-        }
-        DCOL_UNROLL
-        for (int i = 0; i < 3; ++i) {
+        if (c.no_offset) { /* warp-uniform: Q_off = I, r_off = 0 */
             DCOL_UNROLL
-            for (int j = 0; j < 3; ++j) Mq[i][j] = (P::rot ? d[i] * qu[j] + zw[i] * qe[j] : 0.0) + gr[i] * c.r_off[j];
+            for (int i = 0; i < 3; ++i) {
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) Mq[i][j] = P::rot ? d[i] * acc[j] + zw[i] * eh[j] : 0.0;
+            }
+        } else {
+            double qu[3], qe[3];
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                qu[i] = c.Q_off[i][0] * acc[0] + c.Q_off[i][1] * acc[1] + c.Q_off[i][2] * acc[2];
+                qe[i] = c.Q_off[i][0] * eh[0] + c.Q_off[i][1] * eh[1] + c.Q_off[i][2] * eh[2];
+            }
+            DCOL_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                DCOL_UNROLL
+                for (int j = 0; j < 3; ++j) Mq[i][j] = (P::rot ? d[i] * qu[j] + zw[i] * qe[j] : 0.0) + gr[i] * c.r_off[j];
+            }
         }
         g6[0] = gr[0];
         g6[1] = gr[1];

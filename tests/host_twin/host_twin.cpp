@@ -37,8 +37,8 @@ struct RunOne {
         typedef Solver<P1, P2> S;
         typename P1::Const c1;
         typename P2::Const c2;
-        fill_const(*in->s1, in->A, in->b, c1);
-        fill_const(*in->s2, in->A, in->b, c2);
+        fill_const_prim<P1>(*in->s1, in->A, in->b, c1);
+        fill_const_prim<P2>(*in->s2, in->A, in->b, c2);
         S* sv = new S();
         PairResult<S::N> res;
         Trace tr = { out->mu };
