@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -80,15 +81,104 @@ struct Group {
     bool supported;
 };
 
+/* A process-wide cache of the buffers that tables and plans allocate (device memory and the small mapped host buffer of a
+ * plan).  cudaMalloc / cudaFree / cudaHostAlloc / cudaFreeHost take 0.1-1 ms each on a good day and tens to hundreds of
+ * milliseconds on a bad one (measured: tools/diag_teardown.py), and a caller that builds an engine per solve (every
+ * altro_solve) paid ~25 of them.  Freed buffers are parked by (device, kind, size class) and handed out again; at most
+ * kPoolMaxBytes stay parked.  pool_release_all() returns everything to the driver. */
+struct BufPool {
+    struct Key {
+        int device, kind; /* kind 0: device memory, 1: mapped page-locked host memory */
+        size_t bytes;
+        bool operator<(const Key& o) const
+        {
+            return device != o.device ? device < o.device : (kind != o.kind ? kind < o.kind : bytes < o.bytes);
+        }
+    };
+    std::mutex mu;
+    std::multimap<Key, void*> parked;
+    std::map<void*, Key> live;
+    size_t parked_bytes = 0;
+};
+constexpr size_t kPoolMaxBytes = (size_t)3 << 30;
+static BufPool& pool()
+{
+    static BufPool* p = new BufPool(); /* never destroyed: no CUDA calls from a static destructor at process exit */
+    return *p;
+}
+static size_t pool_class(size_t bytes)
+{
+    size_t c = 512;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+static cudaError_t pool_alloc(int device, int kind, size_t bytes, void** out)
+{
+    BufPool& P = pool();
+    const BufPool::Key key = { device, kind, pool_class(bytes ? bytes : 1) };
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.parked.find(key);
+        if (it != P.parked.end()) {
+            *out = it->second;
+            P.parked.erase(it);
+            P.parked_bytes -= key.bytes;
+            P.live[*out] = key;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = kind == 0 ? cudaMalloc(out, key.bytes) : cudaHostAlloc(out, key.bytes, cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return e;
+    }
+    std::lock_guard<std::mutex> lock(P.mu);
+    P.live[*out] = key;
+    return cudaSuccess;
+}
+/* The caller guarantees that no work that touches the buffer is still in flight (the destroy paths synchronise the device
+ * first: a parked buffer may be handed to another owner at once, where cudaFree would have waited). */
+static void pool_free(void* p)
+{
+    if (!p) return;
+    BufPool& P = pool();
+    BufPool::Key key;
+    bool park = false;
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        auto it = P.live.find(p);
+        if (it == P.live.end()) return; /* not ours */
+        key = it->second;
+        P.live.erase(it);
+        if (P.parked_bytes + key.bytes <= kPoolMaxBytes) {
+            P.parked.insert({ key, p });
+            P.parked_bytes += key.bytes;
+            park = true;
+        }
+    }
+    if (!park) {
+        if (key.kind == 0) cudaFree(p);
+        else cudaFreeHost(p);
+    }
+}
+template <class T>
+static cudaError_t pool_alloc_t(int device, size_t count, T** out)
+{
+    void* p = nullptr;
+    cudaError_t e = pool_alloc(device, 0, sizeof(T) * count, &p);
+    *out = (T*)p;
+    return e;
+}
+
 /* scratch of the host-buffer entry point, cached per table and grown on demand */
 struct HostScratch {
     int64_t cap = 0;
     int32_t *idx1 = nullptr, *idx2 = nullptr, *iters = nullptr, *status = nullptr;
     double *pose1 = nullptr, *pose2 = nullptr, *alpha = nullptr, *contact = nullptr, *grad = nullptr;
-    void release()
+    void release() /* back to the pool: nothing may still be using the buffers */
     {
-        cudaFree(idx1); cudaFree(idx2); cudaFree(iters); cudaFree(status);
-        cudaFree(pose1); cudaFree(pose2); cudaFree(alpha); cudaFree(contact); cudaFree(grad);
+        pool_free(idx1); pool_free(idx2); pool_free(iters); pool_free(status);
+        pool_free(pose1); pool_free(pose2); pool_free(alpha); pool_free(contact); pool_free(grad);
         *this = HostScratch();
     }
 };
@@ -517,6 +607,7 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
 {
     if (!T) return;
     DeviceGuard guard_(T->device);
+    cudaDeviceSynchronize(); /* the buffers go back to the pool, which hands them out again without waiting */
     for (int i = 0; i < dcol_shape_table::kSlots; ++i) {
         T->scratch[i].release();
         dcol_plan_destroy(T->plans[i]);
@@ -525,10 +616,10 @@ void dcol_shape_table_destroy(dcol_shape_table* T)
         if (T->ev_done[i]) cudaEventDestroy(T->ev_done[i]);
         if (T->ev_out[i]) cudaEventDestroy(T->ev_out[i]);
     }
-    cudaFree(T->scene_vic[0]);
-    cudaFree(T->scene_vic[1]);
-    cudaFree(T->scene_obs_pose);
-    cudaFree(T->scene_obs_shape);
+    pool_free(T->scene_vic[0]);
+    pool_free(T->scene_vic[1]);
+    pool_free(T->scene_obs_pose);
+    pool_free(T->scene_obs_shape);
     for (int i = 0; i < 4; ++i)
         if (T->streams[i]) cudaStreamDestroy(T->streams[i]);
     for (int i = 0; i < dcol_shape_table::kSlots; ++i)
@@ -672,13 +763,14 @@ static int plan_alloc(const dcol_shape_table* T, int64_t capacity, dcol_plan** o
     P->h_mapped = nullptr;
     P->d_mapped = nullptr;
     P->n_launches = 0;
-    cudaError_t e = cudaMalloc(&P->d_counts, sizeof(int32_t) * ((size_t)ns * ns + 1));
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&P->h_mapped, sizeof(int32_t) * ((size_t)ns * ns + 1), cudaHostAllocMapped);
+    cudaError_t e = pool_alloc_t(T->device, (size_t)ns * ns + 1, &P->d_counts);
+    if (e == cudaSuccess) e = pool_alloc(T->device, 1, sizeof(int32_t) * ((size_t)ns * ns + 1), (void**)&P->h_mapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&P->d_mapped, P->h_mapped, 0);
-    if (e == cudaSuccess && capacity > 0) e = cudaMalloc(&P->d_perm, sizeof(int32_t) * (size_t)capacity);
+    if (e == cudaSuccess && capacity > 0) e = pool_alloc_t(T->device, (size_t)capacity, &P->d_perm);
     if (e != cudaSuccess) {
-        cudaFree(P->d_counts);
-        if (P->h_mapped) cudaFreeHost(P->h_mapped);
+        pool_free(P->d_counts);
+        pool_free(P->h_mapped);
+        pool_free(P->d_perm);
         delete P;
         return fail_cuda(e, "plan allocation");
     }
@@ -708,13 +800,16 @@ void dcol_plan_destroy(dcol_plan* P)
 {
     if (!P) return;
     DeviceGuard guard_(P->device); /* not P->table->device: the table may already have been destroyed */
-    cudaFree(P->d_perm);
-    cudaFree(P->d_perm_alt);
+    /* a solve of this plan may still be in flight on the caller's stream: cudaFree would have waited for it, the pool
+     * does not, so wait here (d_perm may be either of the two permutation buffers after a refine) */
+    cudaDeviceSynchronize();
+    pool_free(P->d_perm);
+    pool_free(P->d_perm_alt);
     cudaFree(P->d_gstart);
     cudaFree(P->d_bins);
-    cudaFree(P->d_counts);
+    pool_free(P->d_counts);
     cudaFree(P->d_state);
-    if (P->h_mapped) cudaFreeHost(P->h_mapped);
+    pool_free(P->h_mapped);
     delete P;
 }
 int64_t dcol_plan_size(const dcol_plan* P) { return P ? P->B : 0; }
@@ -787,7 +882,7 @@ int dcol_plan_refine(dcol_plan* P, const int32_t* d_iters, void* stream_)
     DCOL_DEVICE(P->device);
     (void)cudaGetLastError();
     const int n_bins = n_groups * kRefineBins;
-    if (!P->d_perm_alt) DCOL_CUDA(cudaMalloc(&P->d_perm_alt, sizeof(int32_t) * (size_t)P->capacity));
+    if (!P->d_perm_alt) DCOL_CUDA(pool_alloc_t(P->device, (size_t)P->capacity, &P->d_perm_alt));
     if (P->refine_groups != n_groups) { /* the host entry point rebuilds its cached plans: group lists change */
         cudaFree(P->d_gstart);
         cudaFree(P->d_bins);
@@ -917,15 +1012,16 @@ static int host_pipeline_setup(dcol_shape_table* T, int64_t chunk, int n_slots =
         dcol_plan_destroy(T->plans[i]);
         T->plans[i] = nullptr;
         if (i < 2) T->scene_key[i].clear();
-        cudaError_t e = cudaMalloc(&S.idx1, sizeof(int32_t) * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.idx2, sizeof(int32_t) * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.iters, sizeof(int32_t) * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.status, sizeof(int32_t) * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.pose1, sizeof(double) * 6 * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.pose2, sizeof(double) * 6 * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.alpha, sizeof(double) * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.contact, sizeof(double) * 3 * chunk);
-        if (e == cudaSuccess) e = cudaMalloc(&S.grad, sizeof(double) * 12 * chunk);
+        const int dv = T->device;
+        cudaError_t e = pool_alloc_t(dv, chunk, &S.idx1);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, chunk, &S.idx2);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, chunk, &S.iters);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, chunk, &S.status);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, 6 * chunk, &S.pose1);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, 6 * chunk, &S.pose2);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, chunk, &S.alpha);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, 3 * chunk, &S.contact);
+        if (e == cudaSuccess) e = pool_alloc_t(dv, 12 * chunk, &S.grad);
         if (e != cudaSuccess) { /* no half-allocated slot is left behind */
             S.release();
             return fail_cuda(e, "host scratch allocation");
@@ -1086,22 +1182,22 @@ int dcol_proximity_scene_host(const dcol_shape_table* T_, int32_t victim_shape, 
     if (Mc * n_obs > 0x7fffffffLL) return fail(DCOL_E_ARG, "dcol_proximity_scene_host: too many obstacles");
     if (int rc0 = host_pipeline_setup(T, Mc * n_obs)) return rc0;
     if (T->scene_vic_cap < Mc) {
-        cudaFree(T->scene_vic[0]);
-        cudaFree(T->scene_vic[1]);
+        pool_free(T->scene_vic[0]);
+        pool_free(T->scene_vic[1]);
         T->scene_vic[0] = T->scene_vic[1] = nullptr;
         T->scene_vic_cap = 0;
-        DCOL_CUDA(cudaMalloc(&T->scene_vic[0], sizeof(double) * 6 * Mc));
-        DCOL_CUDA(cudaMalloc(&T->scene_vic[1], sizeof(double) * 6 * Mc));
+        DCOL_CUDA(pool_alloc_t(T->device, (size_t)(6 * Mc), &T->scene_vic[0]));
+        DCOL_CUDA(pool_alloc_t(T->device, (size_t)(6 * Mc), &T->scene_vic[1]));
         T->scene_vic_cap = Mc;
     }
     if (T->scene_obs_cap < n_obs) {
-        cudaFree(T->scene_obs_pose);
-        cudaFree(T->scene_obs_shape);
+        pool_free(T->scene_obs_pose);
+        pool_free(T->scene_obs_shape);
         T->scene_obs_pose = nullptr;
         T->scene_obs_shape = nullptr;
         T->scene_obs_cap = 0;
-        DCOL_CUDA(cudaMalloc(&T->scene_obs_pose, sizeof(double) * 6 * n_obs));
-        DCOL_CUDA(cudaMalloc(&T->scene_obs_shape, sizeof(int32_t) * n_obs));
+        DCOL_CUDA(pool_alloc_t(T->device, (size_t)(6 * n_obs), &T->scene_obs_pose));
+        DCOL_CUDA(pool_alloc_t(T->device, (size_t)n_obs, &T->scene_obs_shape));
         T->scene_obs_cap = n_obs;
     }
     cudaStream_t s_in = T->streams[0], s_run = T->streams[2], s_out = T->streams[3];
