@@ -20,11 +20,19 @@
  *     primitive, and Gram matrices / adjoint products are accumulated in the local frame and
  *     rotated once.  Second-order-cone rows of ball-like primitives are carried in body-frame
  *     components (a rotation of the cone's vector part commutes with every cone operation).
- *  2. Scaled-space Newton step.  With lambda = W z = W^-1 s, the directions are carried as
- *     ds~ = W^-1 ds and dz~ = W dz.  Both line searches then run against lambda (W is an
- *     automorphism of the cone), the orthant needs one rsqrt per row per iteration instead of
- *     ~8 divisions/square roots, and the centring ratio uses <ds, dz> = <ds~, dz~>.
- *  3. W^-1 of a second-order cone in closed form (1/eta) J Wbar J, no Cholesky of W.
+ *  2. Scaled-space Newton step on the second-order cones.  With lambda = W z = W^-1 s, the
+ *     directions are carried as ds~ = W^-1 ds and dz~ = W dz; both line searches then run against
+ *     lambda (W is an automorphism of the cone) and the centring ratio uses <ds, dz> = <ds~, dz~>.
+ *     On the ORTHANT the scaled directions are never formed: the relative steps ds_i / s_i and
+ *     dz_i / z_i are the line-search measures themselves, every product with w_i or lambda_i
+ *     collapses into 1 / s_i and z_i / s_i, and one rcp(s_i z_i) per row per iteration replaces
+ *     the reference's ~8 divisions / square roots (pass_a .. pass_d).
+ *  3. W^-1 of a second-order cone in closed form (1/eta) J Wbar J, no Cholesky of W; rz of a cone
+ *     block stays unscaled and the slack is updated with the primal equation's own ds; the two
+ *     affine line searches share one norm (soc_ls_affine).
+ *  4. The Newton systems are factored as L D L^T (ldlt): same pivots, same tests, shorter
+ *     dependent chains.  The initial point's normal equations come from a shape constant
+ *     (ShapeConst::G0, init_accumulate).
  *
  * Rounding therefore differs from NumPy at the 1e-16 level per operation; SURVEY.md section 0
  * measured that such noise moves alpha by <= 2e-14 and never flips an iteration count.
