@@ -1070,7 +1070,8 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
      * that chunk's own histogram, so chunk i+1 is copied in and planned while chunk i is being solved and
      * chunk i-1 is being copied out. */
     cudaStream_t s_in = T->streams[0], s_plan = T->streams[1], s_out = T->streams[3];
-    const bool one_run_stream = getenv("DCOL_HOST_ONE_RUN_STREAM") != nullptr; /* A/B switch of tools/diag_e2e.py */
+    const bool one_run_stream = getenv("DCOL_HOST_ONE_RUN_STREAM") != nullptr; /* A/B switches of tools/diag_e2e.py */
+    const bool device_count = getenv("DCOL_HOST_DEVICE_COUNT") != nullptr;     /* histogram on the device (with a host wait per chunk) */
     int rc = 0;
     const int64_t n_chunks = (B + chunk - 1) / chunk;
     /* DCOL_HOST_TRACE=1: device timeline of every chunk's stages and the host's enqueue times on stderr (diagnostic) */
@@ -1108,7 +1109,8 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
         DCOL_CUDA_BREAK(cudaMemcpyAsync(S.pose2, pose2 + 6 * k0, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s_in));
         mark(s_in);
         DCOL_CUDA_BREAK(cudaStreamWaitEvent(s_plan, T->ev_in[slot], 0));
-        rc = plan_build_host_counts(P, idx1 + k0, idx2 + k0, S.idx1, S.idx2, n, s_plan);
+        rc = device_count ? plan_build(P, S.idx1, S.idx2, n, s_plan)
+                          : plan_build_host_counts(P, idx1 + k0, idx2 + k0, S.idx1, S.idx2, n, s_plan);
         if (rc) break;
         if (trace) thost.push_back(now_ms() - host0);
         DCOL_CUDA_BREAK(cudaEventRecord(T->ev_plan[slot], s_plan));

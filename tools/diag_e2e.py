@@ -32,9 +32,9 @@ for noprio in ((True, False) if '--prio-ab' in sys.argv else (False,)):
     else:
         os.environ.pop("DCOL_HOST_NOPRIO", None)
     eng = d.ProximityEngine(shapes)   # the host pipeline's streams are created per table
-    for slots in ((2, 4) if '--slots-ab' in sys.argv else (4,)):
+    for slots in ((2, 4) if '--slots-ab' in sys.argv else (int(os.environ.get('DCOL_HOST_SLOTS', 4)),)):
         os.environ["DCOL_HOST_SLOTS"] = str(slots)
-        for chunk in (1 << 17, 1 << 18, 1 << 19, 1 << 20):
+        for chunk in ([int(sys.argv[sys.argv.index('--only-chunk') + 1])] if '--only-chunk' in sys.argv else (1 << 17, 1 << 18, 1 << 19, 1 << 20)):
             os.environ["DCOL_HOST_CHUNK"] = str(chunk)
             eng.solve_host(hi1, hi2, hp1, hp2, out=out)
             eng.solve_host(hi1, hi2, hp1, hp2, out=out)
