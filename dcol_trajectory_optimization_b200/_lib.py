@@ -25,7 +25,7 @@ SYMBOLS = (
     "dcol_plan_create", "dcol_plan_destroy", "dcol_plan_size", "dcol_plan_n_groups", "dcol_plan_n_launches", "dcol_plan_refine",
     "dcol_proximity_batch_device", "dcol_proximity_batch_jacobian", "dcol_proximity_batch_host",
     "dcol_proximity_scene_host", "dcol_host_alloc",
-    "dcol_host_free",
+    "dcol_host_free", "dcol_release_cached",
     "dcol_proximity_batch_records", "dcol_plan_perm", "dcol_device_alloc", "dcol_device_free", "dcol_ipc_export",
     "dcol_ipc_import", "dcol_ipc_close",
     "dcol_debug_trace_pair", "dcol_measure_fp64_peak",
@@ -108,6 +108,8 @@ def lib():
     L.dcol_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.dcol_host_free.restype = None
     L.dcol_host_free.argtypes = [vp]
+    L.dcol_release_cached.restype = None
+    L.dcol_release_cached.argtypes = []
     L.dcol_debug_trace_pair.restype = C.c_int
     L.dcol_debug_trace_pair.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, C.c_double, dp, dp, dp, dp, ip, ip, ip, ip, dp]
     L.dcol_measure_fp64_peak.restype = C.c_int

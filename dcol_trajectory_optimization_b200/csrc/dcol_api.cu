@@ -1319,6 +1319,26 @@ void dcol_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+void dcol_release_cached(void)
+{
+    BufPool& P = pool();
+    std::multimap<BufPool::Key, void*> take;
+    {
+        std::lock_guard<std::mutex> lock(P.mu);
+        take.swap(P.parked);
+        P.parked_bytes = 0;
+    }
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (auto& kv : take) {
+        if (cudaSetDevice(kv.first.device) != cudaSuccess) continue;
+        if (kv.first.kind == 0) cudaFree(kv.second);
+        else cudaFreeHost(kv.second);
+    }
+    if (have_cur) cudaSetDevice(cur);
+    cudaGetLastError();
+}
+
 int dcol_debug_trace_pair(const dcol_shape_table* T, int32_t idx1, int32_t idx2, const double* pose1, const double* pose2,
                           double tol, double* alpha, double* x, double* s, double* z, int32_t* n, int32_t* m,
                           int32_t* iters, int32_t* status, double* mu_trace)

@@ -373,6 +373,12 @@ def pinned_free(arr):
 _PINNED: dict = {}
 
 
+def release_cached():
+    """Hand the device scratch that destroyed engines / plans left in the library's cache back to the driver
+    (``dcol_release_cached``)."""
+    _lib.lib().dcol_release_cached()
+
+
 def measure_fp64_peak(device: int = 0) -> float:
     """Measured FP64 FMA throughput of the device in FLOP/s (the roofline denominator)."""
     v = C.c_double()

@@ -219,6 +219,12 @@ int dcol_proximity_batch_host(const dcol_shape_table* table, const int32_t* idx1
 int  dcol_host_alloc(size_t bytes, void** out);
 void dcol_host_free(void* p);
 
+/* Tables and plans take their device scratch from a process-wide cache inside the library and return it there when
+ * they are destroyed (cudaMalloc / cudaFree cost milliseconds; a caller that builds a table per solve would pay them every
+ * time).  At most 3 GiB stay cached.  This call hands everything that is cached back to the driver; buffers of live tables
+ * and plans are not touched.  (No counterpart in the reference, which has no device memory.) */
+void dcol_release_cached(void);
+
 /* Debug aid: solve ONE pair and also return the per-iteration mu = s'z/deg trace
  * (mu_trace[DCOL_MAX_ITER + 1], NaN padded) and the final (x[8], s[72], z[72]).  Host pointers. */
 int dcol_debug_trace_pair(const dcol_shape_table* table, int32_t idx1, int32_t idx2, const double* pose1,

@@ -149,6 +149,46 @@ def test_device_api_matches_host_api_and_plan_reuse(dcol):
     eng.close()
 
 
+def test_host_entry_many_chunks_slot_rotation_and_pool(dcol):
+    """The pair-list host entry point over many chunks (more chunks than chunk slots, ragged last chunk, host-side
+    histogram per chunk) gives bit for bit what the one-chunk call and the device API give; an out-of-range shape index in
+    a LATE chunk is reported and leaves nothing in flight; engines built one after the other reuse pooled buffers."""
+    import os
+    import torch
+    from dcol_trajectory_optimization_b200 import workloads as W
+    shapes, i1, i2, p1, p2 = W.config4_batch(21_013, seed=5)
+    old = {k: os.environ.get(k) for k in ("DCOL_HOST_CHUNK", "DCOL_HOST_SLOTS")}
+    try:
+        os.environ.pop("DCOL_HOST_CHUNK", None)
+        eng = dcol.ProximityEngine(shapes)
+        one = eng.solve_host(i1, i2, p1, p2)                      # a single chunk
+        eng.close()
+        for chunk, slots in (("2048", "4"), ("2048", "2"), ("1500", "3")):   # 11 / 11 / 15 chunks
+            os.environ["DCOL_HOST_CHUNK"], os.environ["DCOL_HOST_SLOTS"] = chunk, slots
+            eng = dcol.ProximityEngine(shapes)                    # takes the previous engine's buffers from the pool
+            for _ in range(2):                                    # second call: every slot is reused
+                many = eng.solve_host(i1, i2, p1, p2)
+                for f in ("status", "iters", "alpha", "grad", "contact"):
+                    assert np.array_equal(getattr(many, f), getattr(one, f), equal_nan=True), (chunk, slots, f)
+            bad = i2.copy()
+            bad[-7] = len(shapes)                                 # last chunk
+            with pytest.raises(dcol.engine._lib.DcolError):
+                eng.solve_host(i1, bad, p1, p2)
+            again = eng.solve_host(i1, i2, p1, p2)                # the engine is still usable
+            assert np.array_equal(again.alpha, one.alpha)
+            eng.close()
+        dcol.release_cached()                                     # the pool goes back to the driver; new engines still work
+        eng = dcol.ProximityEngine(shapes)
+        assert np.array_equal(eng.solve_host(i1, i2, p1, p2).alpha, one.alpha)
+        eng.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def test_empty_and_single(dcol):
     import torch
     eng = dcol.ProximityEngine([dcol.SphereMRP(0.5), dcol.SphereMRP(0.25)])
