@@ -958,9 +958,23 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
     for (int i = 0; i < n_groups; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P->groups[a].count > P->groups[b].count; });
     int rc = 0;
+    /* DCOL_SOLVE_TRACE=1 (diagnostic, synchronises): start / end of every group's kernel on the device, on stderr */
+    const bool trace = getenv("DCOL_SOLVE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t tev0 = nullptr;
+    if (trace) {
+        cudaEventCreate(&tev0);
+        cudaEventRecord(tev0, stream);
+    }
     for (int oi = 0; oi < n_groups && rc == 0; ++oi) {
         const Group& g = P->groups[order[oi]];
         cudaStream_t st = n_side ? T->side[oi % n_side] : stream;
+        if (trace) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            tev.push_back(e);
+        }
         BatchArgs a = { P->d_perm, g.first, g.count, d_pose1, d_pose2, tol, max_iter, flags,
                         d_alpha, d_contact, d_grad, d_iters, d_status, nullptr, n_dest, record_offset, {} };
         for (int d = 0; d < n_dest; ++d) a.dest[d] = dest[d];
@@ -976,6 +990,26 @@ static int solve_plan(const dcol_plan* P, const double* d_pose1, const double* d
             e = launch_group(T, g.i1, g.i2, a, st);
         }
         if (e != cudaSuccess) rc = fail_cuda(e, "pair_kernel launch");
+        if (trace) {
+            cudaEvent_t e2;
+            cudaEventCreate(&e2);
+            cudaEventRecord(e2, st);
+            tev.push_back(e2);
+        }
+    }
+    if (trace) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "solve trace: %d groups on %d side streams; per group: stream, pairs, classes, start us, end us\n", n_groups, n_side);
+        for (int oi = 0; 2 * oi + 1 < (int)tev.size(); ++oi) {
+            const Group& g = P->groups[order[oi]];
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tev0, tev[2 * oi]);
+            cudaEventElapsedTime(&b, tev0, tev[2 * oi + 1]);
+            fprintf(stderr, "  %2d  s%-2d %8lld  (%d,%d)  %9.1f %9.1f  dur %8.1f\n", oi, n_side ? oi % n_side : 0, (long long)g.count,
+                    T->cls[g.i1], T->cls[g.i2], a * 1e3, b * 1e3, (b - a) * 1e3);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+        cudaEventDestroy(tev0);
     }
     for (int i = 0; i < n_side; ++i) { /* join even after a failed launch: nothing may outlive the call's stream order */
         cudaError_t e = cudaEventRecord(T->join_ev[i], T->side[i]);
@@ -1055,10 +1089,10 @@ int dcol_proximity_batch_host(const dcol_shape_table* T_, const int32_t* idx1, c
     DCOL_DEVICE(T->device);
     const int64_t gw = (flags & DCOL_WANT_GRAD1) ? 6 : 12; /* doubles of gradient per pair */
     /* Chunk size, measured on B200 + PCIe 5 (tools/diag_e2e.py, tools/diag_host_trace.py; profiles/r02_host_pipeline.md):
-     * the call takes about copy-in + solve of ONE chunk plus the copy-out of everything (the slower direction), so smaller
-     * chunks would be better — but a chunk's solve is 40 small grids on 8 streams whose tails leave the SMs half empty
-     * (2^18 pairs: 1.0 ms instead of 0.37 ms), and below 2^20 pairs the solve, not PCIe, sets the period */
-    int64_t kChunk = 1 << 20;
+     * the call takes about the copy-in of everything plus solve and copy-out of ONE chunk, so smaller chunks are better —
+     * until the solves, whose 40 small grids cost a fixed ~0.55 ms per chunk on top of ~1.07 us per 1,000 pairs, take
+     * longer in total than the copies (2^19 pairs: 16 x 1.19 ms against 18.8 ms; 2^18: 32 x 0.86 ms) */
+    int64_t kChunk = 1 << 19;
     int n_slots = dcol_shape_table::kSlots;
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     if (const char* env = getenv("DCOL_HOST_SLOTS")) n_slots = std::max(2, std::min(atoi(env), (int)dcol_shape_table::kSlots));
