@@ -517,6 +517,7 @@ struct Block {
     double kq[P::QA];  /* k = lambda^-1 o (ds~ o dz~), later the corrector's dz~            */
     double wh[P::QA]; /* J wbar = (wbar_0, -wbar_v): W^-1 = (1/eta) Wbar(wh), W = eta Wbar(J wh) */
     double eta, ieta, bw;
+    double iJs; /* 1 / J(s): W^-1 lambda^-1 = (W lambda)^-1 = s^-1 = (s_0, -s_v) / J(s), pass_a */
     double ls_isn, ls_inu, ls_c0; /* shared line-search terms of lambda, pdip.py:39-47      */
     double irho, il0;             /* 1 / J(lambda), 1 / lambda_0, pdip.py:108-118           */
 };
@@ -818,6 +819,7 @@ struct Solver {
             sz += dq;
             const double Js = socJ<P::Q>(B.sq), Jz = socJ<P::Q>(B.zq);
             const double rs = rsqrt_(Js), rz = rsqrt_(Jz);
+            B.iJs = rs * rs;
             /* gamma = sqrt((1 + zbar.sbar) / 2);  wbar = (sbar + J zbar) / (2 gamma) */
             const double g2 = 0.5 * (1.0 + dq * (rs * rz));
             const double ig = 0.5 * rsqrt_(g2);
@@ -873,11 +875,9 @@ struct Solver {
             /* lambda = W z */
             wbar_apply<P::Q>(B.wh, B.bw, -1.0, B.zq, B.eta, B.lam);
             /* rz = s + (G x - h) is kept UNSCALED (in tq): the Newton steps need W^-1 (G dx + rz) = G~ dx + rho~ and the
-             * update of s needs ds = -(G dx + rz) itself (primal equation), so rho~ = W^-1 rz is only a temporary here */
-            double rho[P::QA];
+             * update of s needs ds = -(G dx + rz) itself (primal equation); rho~ = W^-1 rz is only a temporary below */
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) B.tq[i] = B.sq[i] + rq[i];
-            wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.tq, B.ieta, rho); /* rho~ = W^-1 rz */
             /* W^-2 for the Gram block.  Wbar(w)^2 = 2 w w^T - J for w^T J w = 1, so
              * W^-2 = (2 wh wh^T - J) / eta^2: ten products instead of forming W^-1 and squaring it. */
             double W2[P::QA][P::QA];
@@ -900,15 +900,21 @@ struct Solver {
             B.ls_isn = rsqrt_(nu);
             B.ls_inu = B.ls_isn * B.ls_isn;
             B.ls_c0 = rcp_(B.lam[0] * B.ls_isn + 1.0);
-            /* -W^-1 rho~ and W^-1 (lambda^-1 o e), lambda^-1 o e = (lambda_0, -lambda_v) / J(lambda) */
-            double t1[P::QA], t2[P::QA];
-            DCOL_UNROLL
-            for (int i = 0; i < P::Q; ++i) {
-                t1[i] = -rho[i];
-                t2[i] = (i == 0 ? B.lam[i] : -B.lam[i]) * B.irho;
+            /* the right-hand-side share of the centring term needs no W^-1: W^-1 lambda^-1 = (W lambda)^-1 = s^-1 =
+             * (s_0, -s_v) / J(s)  (W is a symmetric automorphism of the cone: (W u)^-1 = W^-1 u^-1, and W lambda = W W^-1 s = s;
+             * on the orthant the same identity is 1 / (w lambda) = 1 / s) */
+            {
+                /* -W^-1 rho~ by two applications of W^-1: the product with the W^-2 above would save one of them, but W^-2
+                 * squares wh, which is large for iterates near the cone's boundary (measured on the host twin: the largest
+                 * gradient deviation from the oracle over 20,000 pairs goes from 7e-8 to 1.2e-7) */
+                double rho[P::QA], t1[P::QA];
+                wbar_apply<P::Q>(B.wh, B.bw, 1.0, B.tq, B.ieta, rho); /* rho~ = W^-1 rz */
+                DCOL_UNROLL
+                for (int i = 0; i < P::Q; ++i) t1[i] = -rho[i];
+                wbar_apply<P::Q>(B.wh, B.bw, 1.0, t1, B.ieta, qa);
             }
-            wbar_apply<P::Q>(B.wh, B.bw, 1.0, t1, B.ieta, qa);
-            wbar_apply<P::Q>(B.wh, B.bw, 1.0, t2, B.ieta, ql);
+            DCOL_UNROLL
+            for (int i = 0; i < P::Q; ++i) ql[i] = (i == 0 ? B.sq[i] : -B.sq[i]) * B.iJs;
         }
         P::soc_apply_t(c, qa, acc_a);
         P::soc_apply_t(c, ql, acc_l);
