@@ -932,14 +932,16 @@ struct Solver {
         DCOL_UNROLL
         for (int i = 1; i < P::Q; ++i) zeta -= B.lam[i] * d[i];
         const double rho0 = zeta * B.ls_inu;
-        const double coef = (zeta * B.ls_isn + d[0]) * B.ls_c0;
+        /* rho_v = d_v / sqrt(nu) - coef lambda_v / nu = (d_v - (coef / sqrt(nu)) lambda_v) / sqrt(nu): the common factor
+         * 1 / sqrt(nu) > 0 leaves the norm once */
+        const double cs = ((zeta * B.ls_isn + d[0]) * B.ls_c0) * B.ls_isn;
         double nn = 0.0;
         DCOL_UNROLL
         for (int i = 1; i < P::Q; ++i) {
-            const double rv = d[i] * B.ls_isn - coef * (B.lam[i] * B.ls_inu);
+            const double rv = fma(-cs, B.lam[i], d[i]);
             nn += rv * rv;
         }
-        return sqrt_(nn) - rho0;
+        return sqrt_(nn) * B.ls_isn - rho0;
     }
     /* The two searches of the AFFINE step at once.  There ds~ + dz~ = -lambda, and with nu = J(lambda)
      * the vector part of rho(ds~) is minus that of rho(dz~): zeta_s = -nu - zeta_z, coef_s = -sqrt(nu) - coef_z, so
@@ -958,14 +960,14 @@ struct Solver {
             zeta_z -= B.lam[i] * dz[i];
             zeta_s -= B.lam[i] * ds[i];
         }
-        const double coef = (zeta_z * B.ls_isn + dz[0]) * B.ls_c0;
+        const double cs = ((zeta_z * B.ls_isn + dz[0]) * B.ls_c0) * B.ls_isn;
         double nn = 0.0;
         DCOL_UNROLL
         for (int i = 1; i < P::Q; ++i) {
-            const double rv = dz[i] * B.ls_isn - coef * (B.lam[i] * B.ls_inu);
+            const double rv = fma(-cs, B.lam[i], dz[i]);
             nn += rv * rv;
         }
-        const double r = sqrt_(nn);
+        const double r = sqrt_(nn) * B.ls_isn;
         mz = r - zeta_z * B.ls_inu;
         ms = r - zeta_s * B.ls_inu;
     }
@@ -1006,7 +1008,6 @@ struct Solver {
             for (int i = 0; i < P::Q; ++i) {
                 ds[i] = -g[i];
                 dz[i] = g[i] - B.lam[i]; /* ds~ + dz~ = -lambda (complementarity) */
-                d_sz += ds[i] * dz[i];
             }
             {
                 double ms, mz;
@@ -1018,6 +1019,7 @@ struct Solver {
             w[0] = 0.0;
             DCOL_UNROLL
             for (int i = 0; i < P::Q; ++i) w[0] += ds[i] * dz[i];
+            d_sz += w[0]; /* <ds~, dz~> of this block is the scalar part of the cone product */
             DCOL_UNROLL
             for (int i = 1; i < P::Q; ++i) w[i] = ds[0] * dz[i] + dz[0] * ds[i];
             double nu = 0.0;
