@@ -247,15 +247,15 @@ struct StateLayout {
     static constexpr int SQ1 = RI1 + F1::NO;
     static constexpr int ZQ1 = SQ1 + F1::Q;
     static constexpr int WH1 = ZQ1 + F1::Q;
-    static constexpr int SC1 = WH1 + F1::Q; /* eta, ieta, bw, 1 / J(s) */
-    static constexpr int SO2 = SC1 + (F1::Q > 0 ? 4 : 0);
+    static constexpr int SC1 = WH1 + F1::Q; /* eta, ieta, bw */
+    static constexpr int SO2 = SC1 + (F1::Q > 0 ? 3 : 0);
     static constexpr int ZO2 = SO2 + F2::NO;
     static constexpr int RI2 = ZO2 + F2::NO;
     static constexpr int SQ2 = RI2 + F2::NO;
     static constexpr int ZQ2 = SQ2 + F2::Q;
     static constexpr int WH2 = ZQ2 + F2::Q;
     static constexpr int SC2 = WH2 + F2::Q;
-    static constexpr int POSE = SC2 + (F2::Q > 0 ? 4 : 0); /* Qp[9], rp[3] of the primitive that is not the frame */
+    static constexpr int POSE = SC2 + (F2::Q > 0 ? 3 : 0); /* Qp[9], rp[3] of the primitive that is not the frame */
     static constexpr int SZ = POSE + 12;
     static constexpr int META = SZ + 1; /* iteration count | status << 8 | finished << 16 */
     static constexpr int POSES = META + 1; /* the pair's two input poses (12 doubles): init_kernel gathers them through the
@@ -283,7 +283,6 @@ __device__ __forceinline__ void visit_block(Block<P>& B, int so, int zo, int ri,
         f(sc + 0, B.eta, false);
         f(sc + 1, B.ieta, false);
         f(sc + 2, B.bw, false);
-        f(sc + 3, B.iJs, false);
     }
 }
 template <class S, class F>
