@@ -78,6 +78,24 @@ def test_twin_analytic_gradient_matches_oracle_exact_gradient(twin, oracle):
     assert gerr.max() < 1e-7 and np.median(gerr) < 1e-10
 
 
+def test_twin_gradient_error_tail_on_the_scene_workload(twin, oracle):
+    """Guards the ROUNDING-level closeness to the reference's iterate path (profiles/r02_arithmetic_parity.md): identities
+    that are exact in exact arithmetic can still fatten the gradient-error tail.  The rejected `s^-1` form of the cone
+    centring term puts ~40 pairs per million of this workload above 1e-7 (largest 1.3e-6); the kernel's arithmetic has none
+    in 8 million (largest 4e-8)."""
+    from dcol_trajectory_optimization_b200 import workloads as W
+    from dcol_trajectory_optimization_b200.shapes import flatten_shapes
+    shapes, i1, i2, p1, p2 = W.config5_batch(n_obs=1024, n_knots=100, n_cand=2, seed=778)       # 204,800 pairs
+    rec, A, b = flatten_shapes(shapes)
+    ref = oracle.solve_batch(rec, A, b, i1, i2, p1, p2, grad_mode=oracle.GRAD_EXACT)
+    out = twin.solve_batch(rec, A, b, i1, i2, p1, p2)
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["iters"], ref["iters"])
+    gerr = np.abs(out["grad"] - ref["grad"]).max(axis=1) / np.abs(ref["grad"]).max(axis=1)
+    aerr = np.abs(out["alpha"] - ref["alpha"]) / np.maximum(np.abs(ref["alpha"]), 1.0)
+    assert gerr.max() < 1e-7 and int((gerr > 3e-8).sum()) <= 2, (gerr.max(), int((gerr > 3e-8).sum()))
+    assert aerr.max() < 1e-10
+
+
 def test_twin_trace_world_frame_sz(twin):
     """(x, s, z) exported in the reference's world-frame row order, and the mu trace."""
     g = load_golden("scenarios")
