@@ -1212,7 +1212,7 @@ int dcol_proximity_scene_host(const dcol_shape_table* T_, int32_t victim_shape, 
         if (obstacle_shape[j] < 0 || obstacle_shape[j] >= ns) return fail(DCOL_E_INDEX, "shape index out of range");
     std::lock_guard<std::mutex> lock(T->mu);
     DCOL_DEVICE(T->device);
-    int64_t kChunk = 1 << 20;
+    int64_t kChunk = 1 << 19; /* measured (tools/diag_scene.py, config 5): 2^18 11.6 ms, 2^19 10.75, 2^20 11.15, 2^21 12.2 per 8.3 M pairs */
     if (const char* env = getenv("DCOL_HOST_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(env));
     const int64_t Mc = std::max<int64_t>(1, std::min<int64_t>(M, kChunk / n_obs)); /* victim poses per chunk */
     if (Mc * n_obs > 0x7fffffffLL) return fail(DCOL_E_ARG, "dcol_proximity_scene_host: too many obstacles");
