@@ -440,7 +440,7 @@ def main():
             eng.solve_host(hi1, hi2, hp1, hp2, out=hout)
         barrier()
         t = time.perf_counter()
-        n_e2e = max(3, args.steps // 2)
+        n_e2e = max(10, args.steps)      # ~22 ms each: the mean over a quarter of a second is stable against host hiccups
         for _ in range(n_e2e):
             eng.solve_host(hi1, hi2, hp1, hp2, out=hout)
         torch.cuda.synchronize()
@@ -476,7 +476,7 @@ def main():
         for _ in range(2):
             eng5.solve_scene_host(0, hv, obs_shape, obs_pose, out=sout)
         t = time.perf_counter()
-        n_rep = max(3, args.steps // 2)
+        n_rep = max(10, args.steps)
         for _ in range(n_rep):
             eng5.solve_scene_host(0, hv, obs_shape, obs_pose, out=sout)
         dt5 = (time.perf_counter() - t) / n_rep
